@@ -1,0 +1,178 @@
+"""Mint golden input/output vectors FROM THE REFERENCE ITSELF -- run in the build container only.
+
+    python oracle/gen_golden.py            # needs /root/reference; writes tests/golden/*.npz
+
+The reference (pure Python, `/root/reference`) cannot travel to the GPU box, and ships no golden
+vectors of its own for this path.  This script imports the reference's unmodified
+modules (`crowd_nav.policy.graph_model.RGL`, `value_estimator.ValueEstimator`,
+`state_predictor.StatePredictor`, and -- with stubs for the absent simulator deps gym /
+matplotlib / rvo2 / socialforce -- `model_predictive_rl.ModelPredictiveRL`), seeds them as
+SURVEY.md §8(d) prescribes, runs them on CPU in fp32 and fp64, and stores weights, inputs and
+outputs as small .npz fixtures.  Nothing here is copied from the reference; it is only executed.
+"""
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = os.environ.get('RGL_REFERENCE', '/root/reference')
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+OUT = os.path.join(ROOT, 'tests', 'golden')
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+
+from relationalgraphlearning_b200.synthetic import synthetic_states  # noqa: E402
+
+
+def load_ref_config(name):
+    path = os.path.join(REF, 'crowd_nav', 'configs', 'icra_benchmark', name + '.py')
+    spec = importlib.util.spec_from_file_location('config', path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def sd_np(sd, prefix):
+    return {prefix + k: v.detach().cpu().numpy() for k, v in sd.items()}
+
+
+def build_modules(seed, layerwise=False, skip=True, scale=None):
+    from crowd_nav.policy.graph_model import RGL
+    from crowd_nav.policy.value_estimator import ValueEstimator
+    from crowd_nav.policy.state_predictor import StatePredictor
+    cfg = load_ref_config('mp_separate').PolicyConfig()
+    cfg.gcn.layerwise_graph = layerwise
+    cfg.gcn.skip_connection = skip
+    torch.manual_seed(seed)
+    g1 = RGL(cfg, 9, 5)
+    ve = ValueEstimator(cfg, g1)
+    g2 = RGL(cfg, 9, 5)
+    sp = StatePredictor(cfg, g2, 0.25)
+    if scale is not None:
+        with torch.no_grad():
+            for g in (g1, g2):
+                g.w_a.mul_(scale)
+                for w in g.Ws:
+                    w.mul_(scale)
+    return cfg, g1, ve, g2, sp
+
+
+def forward_case(name, seed, nh, batch, layerwise=False, skip=True, scale=None, data_seed=1234):
+    cfg, g1, ve, g2, sp = build_modules(seed, layerwise, skip, scale)
+    robot, humans = synthetic_states(batch, nh, seed=data_seed)
+    out = {}
+    with torch.no_grad():
+        H = g1((robot, humans)).clone()
+        A = np.zeros((0, 0), np.float32) if g1.A is None else np.array(g1.A, copy=True)   # layerwise: reference never sets .A
+        V = ve((robot, humans))
+        S = sp((robot, humans), None)[1]
+        g1.double(); ve.double(); g2.double(); sp.double()
+        H64 = g1((robot.double(), humans.double())).clone()
+        V64 = ve((robot.double(), humans.double()))
+        S64 = sp((robot.double(), humans.double()), None)[1]
+        g1.float(); ve.float(); g2.float(); sp.float()
+    out.update(sd_np(g1.state_dict(), 'graph1/'))
+    out.update(sd_np(ve.value_network.state_dict(), 'value/'))
+    out.update(sd_np(g2.state_dict(), 'graph2/'))
+    out.update(sd_np(sp.human_motion_predictor.state_dict(), 'motion/'))
+    out.update(robot=robot.numpy(), humans=humans.numpy(), H=H.numpy(), A0=A, V=V.numpy(), S=S.numpy(),
+               H64=H64.numpy(), V64=V64.numpy(), S64=S64.numpy(),
+               meta=np.array([seed, nh, batch, int(layerwise), int(skip), data_seed], dtype=np.int64),
+               scale=np.array([1.0 if scale is None else scale]))
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
+    print('wrote', name, 'V range', float(V.min()), float(V.max()), '|H|max', float(H.abs().max()))
+
+
+def stub_sim_deps():
+    for name in ('gym', 'gym.envs', 'gym.envs.registration', 'matplotlib', 'matplotlib.pyplot', 'matplotlib.lines',
+                 'matplotlib.animation', 'matplotlib.patches', 'matplotlib.collections', 'rvo2', 'socialforce',
+                 'tensorboardX', 'git'):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__path__ = []
+            sys.modules[name] = m
+    sys.modules['gym'].Env = object
+    sys.modules['gym.envs.registration'].register = lambda **kw: None
+    sys.modules['matplotlib'].lines = sys.modules['matplotlib.lines']
+    sys.modules['matplotlib'].pyplot = sys.modules['matplotlib.pyplot']
+    sys.modules['matplotlib'].animation = sys.modules['matplotlib.animation']
+    sys.modules['matplotlib'].patches = sys.modules['matplotlib.patches']
+    sys.modules['matplotlib'].collections = sys.modules['matplotlib.collections']
+    sys.modules['matplotlib'].use = lambda *a, **k: None
+    sys.modules['matplotlib.collections'].PatchCollection = object
+
+
+def planner_case(name, seed, nh, n_states, data_seed=77):
+    """Depth-1 predict() of the unmodified reference planner on n_states synthetic JointStates."""
+    stub_sim_deps()
+    from crowd_nav.policy.model_predictive_rl import ModelPredictiveRL
+    from crowd_sim.envs.utils.state import FullState, ObservableState, JointState
+    cfg = load_ref_config('mp_separate').PolicyConfig()
+    torch.manual_seed(seed)
+    pol = ModelPredictiveRL()
+    pol.configure(cfg)
+    pol.set_time_step(0.25)
+    pol.set_device(torch.device('cpu'))
+    pol.set_phase('test')
+    robot, humans = synthetic_states(n_states, nh, seed=data_seed)
+    # bring a few states near collision / goal so every reward branch is exercised
+    humans[1, 0, 0:2] = robot[1, 0, 0:2] + torch.tensor([0.55, 0.0])
+    humans[2, 1, 0:2] = robot[2, 0, 0:2] + torch.tensor([0.0, 0.75])
+    robot[3, 0, 0:2] = torch.tensor([0.05, 3.8])
+    chosen, values, rewards, vnext = [], [], [], []
+    with torch.no_grad():
+        for b in range(n_states):
+            r = [float(x) for x in robot[b, 0]]
+            st = JointState(FullState(*r), [ObservableState(*[float(x) for x in humans[b, h]]) for h in range(nh)])
+            act = pol.predict(st)
+            idx = [i for i, a in enumerate(pol.action_space) if a == act][0]
+            chosen.append(idx)
+            vals, rews, vns = [], [], []
+            st_t = st.to_tensor(add_batch_size=True, device=pol.device)
+            for a in pol.action_space:
+                nxt = pol.state_predictor(st_t, a)
+                v, _ = pol.V_planning(nxt, 1, 1)
+                rew = pol.estimate_reward(st, a)
+                rews.append(float(rew))
+                vns.append(float(v))
+                vals.append(float(rew + pol.get_normalized_gamma() * v))
+            values.append(vals); rewards.append(rews); vnext.append(vns)
+            # look-ahead style reward: state given as a tensor tuple (tensor_to_joint_state path)
+    actions = np.array([[a.vx, a.vy] for a in pol.action_space], dtype=np.float64)
+    sd = pol.get_state_dict()
+    out = {}
+    out.update(sd_np(sd['graph_model1'], 'graph1/'))
+    out.update(sd_np(sd['value_network'], 'value/'))
+    out.update(sd_np(sd['graph_model2'], 'graph2/'))
+    out.update(sd_np(sd['motion_predictor'], 'motion/'))
+    out.update(robot=robot.numpy(), humans=humans.numpy(), chosen=np.array(chosen), values=np.array(values),
+               rewards=np.array(rewards), vnext=np.array(vnext), actions=actions,
+               action_group_index=np.array(pol.action_group_index),
+               meta=np.array([seed, nh, n_states, data_seed], dtype=np.int64))
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
+    print('wrote', name, 'chosen', chosen)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(1)
+    forward_case('fwd_nh5_s0', 0, 5, 64)
+    forward_case('fwd_nh5_s1', 1, 5, 64)
+    forward_case('fwd_nh5_s2', 2, 5, 64)
+    forward_case('fwd_nh5_b1', 0, 5, 1, data_seed=5)            # C1: batch 1
+    forward_case('fwd_nh10_s0', 0, 10, 48)
+    forward_case('fwd_nh20_s0', 0, 20, 40)
+    forward_case('fwd_nh1_s0', 0, 1, 33)                       # smallest graph
+    forward_case('fwd_nh5_trained', 1, 5, 64, scale=0.2)       # trained-like logits
+    forward_case('fwd_nh5_adversarial', 2, 5, 64, scale=4.0)   # softmax saturation
+    forward_case('fwd_nh5_layerwise_noskip', 0, 5, 64, layerwise=True, skip=False)   # BasePolicyConfig defaults
+    forward_case('fwd_nh5_layerwise_skip', 1, 5, 64, layerwise=True, skip=True)
+    planner_case('planner_d1_nh5', 0, 5, 8)
+
+
+if __name__ == '__main__':
+    main()
