@@ -1,0 +1,152 @@
+/*
+ * rgl_b200.h -- C ABI of the B200-native RGL hot path (librgl_b200.so).
+ *
+ * The reference (ChanganVR/RelationalGraphLearning) is pure Python/PyTorch and has no FFI; the
+ * entry points below are what a binding for its hot path would bind.  Each one names the
+ * reference interface it replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous row-major fp32 unless said otherwise;
+ *   - the caller owns every buffer; the library allocates nothing persistent;
+ *   - `stream` is a cudaStream_t / CUstream handle (e.g. torch.cuda.current_stream().cuda_stream);
+ *     all work is enqueued on it, there are no hidden synchronisations;
+ *   - return value: 0 on success, a negative RGL_E* code otherwise; nothing throws or exits;
+ *     rgl_last_error_string() gives a thread-local description of the last failure;
+ *   - stateless and re-entrant: safe from several host threads / one process per GPU.
+ *
+ * State layouts (crowd_sim/envs/utils/state.py:27-28,51-52):
+ *   robot [B,1,9]  = (px, py, vx, vy, radius, gx, gy, v_pref, theta)
+ *   humans[B,Nh,5] = (px, py, vx, vy, radius)            n = Nh + 1 graph nodes, node 0 = robot
+ */
+#ifndef RGL_B200_H_
+#define RGL_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RGL_B200_VERSION 100          /* major*10000 + minor*100 + patch */
+
+#define RGL_X_DIM        32           /* config.gcn.X_dim = final_state_dim (configs/icra_benchmark/config.py:103-108) */
+#define RGL_EMB_HIDDEN   64           /* wr_dims[0] = wh_dims[0] */
+#define RGL_ROBOT_DIM    9
+#define RGL_HUMAN_DIM    5
+#define RGL_VALUE_HIDDEN 100          /* value_network_dims = [32,100,100,1] (mp_separate.py:26) */
+#define RGL_MOTION_HIDDEN 64          /* motion_predictor_dims = [64,5]      (mp_separate.py:25) */
+#define RGL_MAX_LAYERS   4
+#define RGL_MAX_HUMANS   31
+
+/* error codes */
+#define RGL_OK            0
+#define RGL_EINVAL       -1           /* null pointer, bad size, unsupported flag combination */
+#define RGL_EALIGN       -2           /* pointer not 16-byte aligned where required */
+#define RGL_ECUDA        -3           /* a CUDA runtime call failed (see rgl_last_error_string) */
+#define RGL_EUNSUPPORTED -4           /* shape outside what the kernels are built for */
+
+/* flags for the graph kernels */
+#define RGL_FLAG_SKIP       1         /* config.gcn.skip_connection  (graph_model.py:126-127) */
+#define RGL_FLAG_LAYERWISE  2         /* config.gcn.layerwise_graph  (graph_model.py:120-122) */
+
+typedef void* rgl_stream_t;
+
+/* Pointers to the tensors of RGL.state_dict() in PyTorch's native layout, zero-copy
+ * (crowd_nav/policy/graph_model.py:41-58; names in SURVEY.md §2b). Linear weights are [out,in]. */
+typedef struct RglGraphParams {
+    const float* wr0_w;   /* w_r.0.weight [64,9]  */
+    const float* wr0_b;   /* w_r.0.bias   [64]    */
+    const float* wr1_w;   /* w_r.2.weight [32,64] */
+    const float* wr1_b;   /* w_r.2.bias   [32]    */
+    const float* wh0_w;   /* w_h.0.weight [64,5]  */
+    const float* wh0_b;   /* w_h.0.bias   [64]    */
+    const float* wh1_w;   /* w_h.2.weight [32,64] */
+    const float* wh1_b;   /* w_h.2.bias   [32]    */
+    const float* w_a;     /* w_a          [32,32] */
+    const float* Ws[RGL_MAX_LAYERS];   /* Ws.i [32,32] */
+    int num_layer;
+} RglGraphParams;
+
+/* value_network state_dict (crowd_nav/policy/value_estimator.py:9): mlp(32,[32,100,100,1]) */
+typedef struct RglValueParams {
+    const float* w0; const float* b0;   /* 0.weight [32,32],   0.bias [32]  */
+    const float* w1; const float* b1;   /* 2.weight [100,32],  2.bias [100] */
+    const float* w2; const float* b2;   /* 4.weight [100,100], 4.bias [100] */
+    const float* w3; const float* b3;   /* 6.weight [1,100],   6.bias [1]   */
+} RglValueParams;
+
+/* human_motion_predictor state_dict (crowd_nav/policy/state_predictor.py:17): mlp(32,[64,5]) */
+typedef struct RglMotionParams {
+    const float* w0; const float* b0;   /* 0.weight [64,32], 0.bias [64] */
+    const float* w1; const float* b1;   /* 2.weight [5,64],  2.bias [5]  */
+} RglMotionParams;
+
+int         rgl_version(void);
+const char* rgl_last_error_string(void);
+
+/* ---- weight packing -------------------------------------------------------------------------
+ * The kernels read weights from one contiguous k-major blob per module (staged into shared
+ * memory with a single TMA bulk copy).  Packing is a tiny gather kernel; redo it after every
+ * optimizer step / load_state_dict.  Sizes are in floats. */
+size_t rgl_packed_graph_floats(int num_layer);
+size_t rgl_packed_value_floats(void);
+size_t rgl_packed_motion_floats(void);
+int rgl_pack_graph (const RglGraphParams*  p, float* packed, rgl_stream_t stream);
+int rgl_pack_value (const RglValueParams*  p, float* packed, rgl_stream_t stream);
+int rgl_pack_motion(const RglMotionParams* p, float* packed, rgl_stream_t stream);
+
+/* ---- fused graph forward ----------------------------------------------------------------------
+ * Replaces RGL.forward (graph_model.py:99-130): embedding MLPs w_r/w_h, A = softmax(X w_a X^T),
+ * num_layer x H' = relu(A H W_i) (+H), all inside one kernel, plus optionally the state-predictor
+ * head (state_predictor.py:28,36).  Any non-null output is produced:
+ *   H  [B,n,32]  final node features                      (RGL.forward return value)
+ *   E  [B,32]    robot row H[:,0,:]                        (value_estimator.py:18)
+ *   S  [B,Nh,5]  human_motion_predictor(H)[:,1:,:]         (needs motion_packed)
+ *   A0 [n,n]     attention of state 0, first graph         (RGL.A, graph_model.py:116)
+ * humans_bcast >= 1: state b reads humans[b / humans_bcast] (the planner evaluates many robot
+ * actions against one human set; 1 = plain batch).  When only E is requested the last layer is
+ * evaluated for the robot row only. */
+int rgl_graph_forward(const float* robot, const float* humans, int B, int Nh, int humans_bcast,
+                      const float* graph_packed, int num_layer, int flags,
+                      const float* motion_packed,
+                      float* H, float* E, float* S, float* A0,
+                      rgl_stream_t stream);
+
+/* Value head: V[B] = value_network(E[B,32]) (value_estimator.py:19). */
+int rgl_value_head(const float* E, int B, const float* value_packed, float* V, rgl_stream_t stream);
+
+/* Convenience: ValueEstimator.forward (value_estimator.py:11-20) = graph forward (E only) + value
+ * head, two launches on `stream`; E_scratch [B,32] is caller-provided. */
+int rgl_value_forward(const float* robot, const float* humans, int B, int Nh, int humans_bcast,
+                      const float* graph_packed, int num_layer, int flags,
+                      const float* value_packed, float* E_scratch, float* V, float* A0,
+                      rgl_stream_t stream);
+
+/* ---- stand-alone GCN layer ----------------------------------------------------------------------
+ * One layer of graph_model.py:119-128 on node features already in HBM:
+ *   Hout = relu((A X) W) (+ X if RGL_FLAG_SKIP), with A given ([B,n,n]) or, when A == NULL,
+ *   computed in-kernel as softmax(X w_a X^T) (w_a [32,32] row-major, W [32,32] row-major,
+ *   both exactly the nn.Parameter layout).  Aout (optional) receives the attention. */
+int rgl_gcn_layer(const float* X, const float* A, const float* W, const float* w_a,
+                  int B, int n, int flags, float* Hout, float* Aout, rgl_stream_t stream);
+
+/* ---- batched look-ahead step (planner inner loop) -------------------------------------------------
+ * For every (state e, action a): next robot state (state_predictor.py:41-60, holonomic) and the
+ * reward estimate (model_predictive_rl.py:304-357 + crowd_sim/envs/utils/utils.py:4-26), in one
+ * launch.  actions: DEVICE double [A,2] = (vx, vy) (model_predictive_rl.py:155-190 builds them in
+ * float64).  Outputs: next_robot [E*A,1,9] fp32 (row e*A+a), reward [E*A] fp32.
+ * Reward arithmetic is float64 on the fp32 state values. */
+int rgl_plan_expand(const float* robot, const float* humans, int E, int Nh,
+                    const double* actions, int A, double time_step,
+                    float* next_robot, float* reward, rgl_stream_t stream);
+
+/* value[e,a] = reward[e,a] + gamma_bar * V[e*A+a] (fp32, same op order as model_predictive_rl.py:227);
+ * best[e] = first index of the maximum (strict '>' scan, model_predictive_rl.py:228-231),
+ * -1 if every value is NaN/-inf. */
+int rgl_plan_argmax(const float* reward, const float* V, int E, int A, float gamma_bar,
+                    float* value, int* best, rgl_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RGL_B200_H_ */

@@ -1,0 +1,98 @@
+"""ctypes binding of librgl_b200.so -- the only way the Python modules reach the sm_100a kernels.
+
+There is deliberately NO fallback: if the library is missing or a call fails, an exception is raised
+(the product path must fail loudly rather than silently compute somewhere else).
+"""
+import ctypes
+import os
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, 'librgl_b200.so')
+
+MAX_LAYERS = 4
+FLAG_SKIP = 1
+FLAG_LAYERWISE = 2
+
+c_float_p = ctypes.c_void_p
+
+
+class GraphParams(ctypes.Structure):
+    _fields_ = [('wr0_w', c_float_p), ('wr0_b', c_float_p), ('wr1_w', c_float_p), ('wr1_b', c_float_p),
+                ('wh0_w', c_float_p), ('wh0_b', c_float_p), ('wh1_w', c_float_p), ('wh1_b', c_float_p),
+                ('w_a', c_float_p), ('Ws', c_float_p * MAX_LAYERS), ('num_layer', ctypes.c_int)]
+
+
+class ValueParams(ctypes.Structure):
+    _fields_ = [('w0', c_float_p), ('b0', c_float_p), ('w1', c_float_p), ('b1', c_float_p),
+                ('w2', c_float_p), ('b2', c_float_p), ('w3', c_float_p), ('b3', c_float_p)]
+
+
+class MotionParams(ctypes.Structure):
+    _fields_ = [('w0', c_float_p), ('b0', c_float_p), ('w1', c_float_p), ('b1', c_float_p)]
+
+
+EXPORTS = {
+    'rgl_version': (ctypes.c_int, []),
+    'rgl_last_error_string': (ctypes.c_char_p, []),
+    'rgl_packed_graph_floats': (ctypes.c_size_t, [ctypes.c_int]),
+    'rgl_packed_value_floats': (ctypes.c_size_t, []),
+    'rgl_packed_motion_floats': (ctypes.c_size_t, []),
+    'rgl_pack_graph': (ctypes.c_int, [ctypes.POINTER(GraphParams), c_float_p, ctypes.c_void_p]),
+    'rgl_pack_value': (ctypes.c_int, [ctypes.POINTER(ValueParams), c_float_p, ctypes.c_void_p]),
+    'rgl_pack_motion': (ctypes.c_int, [ctypes.POINTER(MotionParams), c_float_p, ctypes.c_void_p]),
+    'rgl_graph_forward': (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                         c_float_p, ctypes.c_int, ctypes.c_int, c_float_p,
+                                         c_float_p, c_float_p, c_float_p, c_float_p, ctypes.c_void_p]),
+    'rgl_value_head': (ctypes.c_int, [c_float_p, ctypes.c_int, c_float_p, c_float_p, ctypes.c_void_p]),
+    'rgl_value_forward': (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                         c_float_p, ctypes.c_int, ctypes.c_int, c_float_p, c_float_p, c_float_p,
+                                         c_float_p, ctypes.c_void_p]),
+    'rgl_gcn_layer': (ctypes.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_int, c_float_p, c_float_p, ctypes.c_void_p]),
+    'rgl_plan_expand': (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                       ctypes.c_int, ctypes.c_double, c_float_p, c_float_p, ctypes.c_void_p]),
+    'rgl_plan_argmax': (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                       c_float_p, ctypes.c_void_p, ctypes.c_void_p]),
+}
+
+_lib = None
+
+
+class RglError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load librgl_b200.so (once).  Raises if it has not been built -- no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RglError('librgl_b200.so not found at %s; build it with '
+                           '`python -m relationalgraphlearning_b200.build`' % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in EXPORTS.items():
+            fn = getattr(handle, name)     # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().rgl_last_error_string()
+        raise RglError('%s failed (rc=%d): %s' % (what, rc, msg.decode() if msg else ''))
+
+
+def ptr(t):
+    """Device pointer of a contiguous fp32/fp64/int32 CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), 'librgl_b200 takes contiguous CUDA tensors'
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)

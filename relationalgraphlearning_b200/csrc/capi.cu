@@ -1,0 +1,152 @@
+// extern "C" boundary of librgl_b200.so (declared in include/rgl_b200.h): argument validation, device
+// queries, launches.  No torch types, no exceptions, no hidden synchronisation.
+#include <stdio.h>
+#include <string.h>
+#include "kernels.h"
+
+
+namespace {
+thread_local char g_err[256] = "";
+
+int fail(int code, const char* msg) {
+    snprintf(g_err, sizeof(g_err), "%s", msg);
+    return code;
+}
+int fail_cuda(cudaError_t e, const char* where) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+    return RGL_ECUDA;
+}
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+struct DevInfo { int dev; int sms; size_t max_smem; };
+// queried per call for the current device (cheap attribute reads; no global mutable state to race on)
+int dev_info(DevInfo* d) {
+    cudaError_t e = cudaGetDevice(&d->dev);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaGetDevice");
+    int v = 0;
+    e = cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d->dev);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaDeviceGetAttribute(sm count)");
+    d->sms = v;
+    e = cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, d->dev);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaDeviceGetAttribute(smem optin)");
+    d->max_smem = (size_t)v;
+    return RGL_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int rgl_version(void) { return RGL_B200_VERSION; }
+const char* rgl_last_error_string(void) { return g_err; }
+
+size_t rgl_packed_graph_floats(int num_layer) {
+    if (num_layer < 1 || num_layer > RGL_MAX_LAYERS) return 0;
+    return (size_t)rgl::graph_floats(num_layer);
+}
+size_t rgl_packed_value_floats(void) { return rgl::VALUE_FLOATS; }
+size_t rgl_packed_motion_floats(void) { return rgl::MOTION_FLOATS; }
+
+int rgl_pack_graph(const RglGraphParams* p, float* packed, rgl_stream_t stream) {
+    if (!p || !packed) return fail(RGL_EINVAL, "rgl_pack_graph: null argument");
+    if (p->num_layer < 1 || p->num_layer > RGL_MAX_LAYERS) return fail(RGL_EUNSUPPORTED, "rgl_pack_graph: num_layer out of range");
+    if (!p->wr0_w || !p->wr0_b || !p->wr1_w || !p->wr1_b || !p->wh0_w || !p->wh0_b || !p->wh1_w || !p->wh1_b || !p->w_a)
+        return fail(RGL_EINVAL, "rgl_pack_graph: null parameter tensor");
+    for (int l = 0; l < p->num_layer; ++l)
+        if (!p->Ws[l]) return fail(RGL_EINVAL, "rgl_pack_graph: null Ws tensor");
+    cudaError_t e = rgl::run_pack_graph(*p, packed, (cudaStream_t)stream);
+    return e == cudaSuccess ? RGL_OK : fail_cuda(e, "rgl_pack_graph");
+}
+int rgl_pack_value(const RglValueParams* p, float* packed, rgl_stream_t stream) {
+    if (!p || !packed || !p->w0 || !p->b0 || !p->w1 || !p->b1 || !p->w2 || !p->b2 || !p->w3 || !p->b3)
+        return fail(RGL_EINVAL, "rgl_pack_value: null argument");
+    cudaError_t e = rgl::run_pack_value(*p, packed, (cudaStream_t)stream);
+    return e == cudaSuccess ? RGL_OK : fail_cuda(e, "rgl_pack_value");
+}
+int rgl_pack_motion(const RglMotionParams* p, float* packed, rgl_stream_t stream) {
+    if (!p || !packed || !p->w0 || !p->b0 || !p->w1 || !p->b1) return fail(RGL_EINVAL, "rgl_pack_motion: null argument");
+    cudaError_t e = rgl::run_pack_motion(*p, packed, (cudaStream_t)stream);
+    return e == cudaSuccess ? RGL_OK : fail_cuda(e, "rgl_pack_motion");
+}
+
+int rgl_graph_forward(const float* robot, const float* humans, int B, int Nh, int humans_bcast,
+                      const float* graph_packed, int num_layer, int flags, const float* motion_packed,
+                      float* H, float* E, float* S, float* A0, rgl_stream_t stream) {
+    if (!robot || !humans || !graph_packed) return fail(RGL_EINVAL, "rgl_graph_forward: null input");
+    if (!H && !E && !S) return fail(RGL_EINVAL, "rgl_graph_forward: no output requested");
+    if (S && !motion_packed) return fail(RGL_EINVAL, "rgl_graph_forward: S requested without motion_packed");
+    if (B < 0 || humans_bcast < 1) return fail(RGL_EINVAL, "rgl_graph_forward: bad batch / humans_bcast");
+    if (Nh < 1 || Nh > RGL_MAX_HUMANS) return fail(RGL_EUNSUPPORTED, "rgl_graph_forward: human count outside [1,31]");
+    if (num_layer < 1 || num_layer > RGL_MAX_LAYERS) return fail(RGL_EUNSUPPORTED, "rgl_graph_forward: num_layer out of range");
+    if (flags & ~(RGL_FLAG_SKIP | RGL_FLAG_LAYERWISE)) return fail(RGL_EINVAL, "rgl_graph_forward: unknown flag");
+    if (!aligned16(graph_packed) || (motion_packed && !aligned16(motion_packed)))
+        return fail(RGL_EALIGN, "rgl_graph_forward: packed weights must be 16-byte aligned");
+    if ((H && !aligned16(H)) || (E && !aligned16(E))) return fail(RGL_EALIGN, "rgl_graph_forward: H/E must be 16-byte aligned");
+    if (B == 0) return RGL_OK;
+    DevInfo d;
+    if (int rc = dev_info(&d)) return rc;
+    rgl::GraphArgs a;
+    a.robot = robot; a.humans = humans; a.B = B; a.Nh = Nh; a.hb = humans_bcast;
+    a.gw = graph_packed; a.mw = S ? motion_packed : nullptr; a.L = num_layer; a.flags = flags;
+    a.H = H; a.E = E; a.S = S; a.A0 = A0; a.ntiles = 0;
+    a.use_tma = (humans_bcast == 1 && aligned16(robot) && aligned16(humans)) ? 1 : 0;
+    cudaError_t e = rgl::run_graph_forward(a, d.sms, d.max_smem, (cudaStream_t)stream);
+    if (e == cudaErrorInvalidConfiguration) return fail(RGL_EUNSUPPORTED, "rgl_graph_forward: tile does not fit in shared memory");
+    return e == cudaSuccess ? RGL_OK : fail_cuda(e, "rgl_graph_forward");
+}
+
+int rgl_value_head(const float* E, int B, const float* value_packed, float* V, rgl_stream_t stream) {
+    if (!E || !value_packed || !V || B < 0) return fail(RGL_EINVAL, "rgl_value_head: bad argument");
+    if (!aligned16(value_packed)) return fail(RGL_EALIGN, "rgl_value_head: packed weights must be 16-byte aligned");
+    if (B == 0) return RGL_OK;
+    DevInfo d;
+    if (int rc = dev_info(&d)) return rc;
+    cudaError_t e = rgl::run_value_head(E, B, value_packed, V, aligned16(E) ? 1 : 0, d.sms, (cudaStream_t)stream);
+    return e == cudaSuccess ? RGL_OK : fail_cuda(e, "rgl_value_head");
+}
+
+int rgl_value_forward(const float* robot, const float* humans, int B, int Nh, int humans_bcast,
+                      const float* graph_packed, int num_layer, int flags, const float* value_packed,
+                      float* E_scratch, float* V, float* A0, rgl_stream_t stream) {
+    if (!E_scratch || !V) return fail(RGL_EINVAL, "rgl_value_forward: null output");
+    int rc = rgl_graph_forward(robot, humans, B, Nh, humans_bcast, graph_packed, num_layer, flags, nullptr,
+                               nullptr, E_scratch, nullptr, A0, stream);
+    if (rc) return rc;
+    return rgl_value_head(E_scratch, B, value_packed, V, stream);
+}
+
+int rgl_gcn_layer(const float* X, const float* A, const float* W, const float* w_a, int B, int n, int flags,
+                  float* Hout, float* Aout, rgl_stream_t stream) {
+    if (!X || !W || !Hout || B < 0) return fail(RGL_EINVAL, "rgl_gcn_layer: bad argument");
+    if (!A && !w_a) return fail(RGL_EINVAL, "rgl_gcn_layer: need A or w_a");
+    if (n < 2 || n > RGL_MAX_HUMANS + 1) return fail(RGL_EUNSUPPORTED, "rgl_gcn_layer: n outside [2,32]");
+    if (flags & ~RGL_FLAG_SKIP) return fail(RGL_EINVAL, "rgl_gcn_layer: unknown flag");
+    if (!aligned16(X) || !aligned16(Hout) || !aligned16(W) || (w_a && !aligned16(w_a)))
+        return fail(RGL_EALIGN, "rgl_gcn_layer: X/W/w_a/Hout must be 16-byte aligned");
+    if (B == 0) return RGL_OK;
+    DevInfo d;
+    if (int rc = dev_info(&d)) return rc;
+    cudaError_t e = rgl::run_gcn_layer(X, A, W, w_a, B, n, flags, Hout, Aout, d.sms, d.max_smem, (cudaStream_t)stream);
+    if (e == cudaErrorInvalidConfiguration) return fail(RGL_EUNSUPPORTED, "rgl_gcn_layer: tile does not fit in shared memory");
+    return e == cudaSuccess ? RGL_OK : fail_cuda(e, "rgl_gcn_layer");
+}
+
+int rgl_plan_expand(const float* robot, const float* humans, int E, int Nh, const double* actions, int A, double time_step,
+                    float* next_robot, float* reward, rgl_stream_t stream) {
+    if (!robot || !actions || E < 0 || A < 1 || Nh < 0) return fail(RGL_EINVAL, "rgl_plan_expand: bad argument");
+    if (reward && Nh > 0 && !humans) return fail(RGL_EINVAL, "rgl_plan_expand: reward needs humans");
+    if (!next_robot && !reward) return fail(RGL_EINVAL, "rgl_plan_expand: no output requested");
+    if ((long long)E * A > 0x7fffffffLL) return fail(RGL_EUNSUPPORTED, "rgl_plan_expand: E*A too large");
+    if (E == 0) return RGL_OK;
+    cudaError_t e = rgl::run_plan_expand(robot, humans, E, Nh, actions, A, time_step, next_robot, reward, (cudaStream_t)stream);
+    return e == cudaSuccess ? RGL_OK : fail_cuda(e, "rgl_plan_expand");
+}
+
+int rgl_plan_argmax(const float* reward, const float* V, int E, int A, float gamma_bar, float* value, int* best,
+                    rgl_stream_t stream) {
+    if (!reward || !V || E < 0 || A < 1 || (!value && !best)) return fail(RGL_EINVAL, "rgl_plan_argmax: bad argument");
+    if (E == 0) return RGL_OK;
+    cudaError_t e = rgl::run_plan_argmax(reward, V, E, A, gamma_bar, value, best, (cudaStream_t)stream);
+    return e == cudaSuccess ? RGL_OK : fail_cuda(e, "rgl_plan_argmax");
+}
+
+}  // extern "C"

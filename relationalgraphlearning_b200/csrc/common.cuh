@@ -1,0 +1,147 @@
+// Shared device helpers + packed-weight layout for the RGL sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/rgl_b200.h"
+
+namespace rgl {
+
+constexpr int XD  = RGL_X_DIM;          // 32
+constexpr int HID = RGL_EMB_HIDDEN;     // 64
+constexpr int RD  = RGL_ROBOT_DIM;      // 9
+constexpr int HD  = RGL_HUMAN_DIM;      // 5
+constexpr int LDX = XD + 4;             // padded smem row stride (floats): 36 = 4 mod 32 -> 8 consecutive
+                                        // rows x 16 B hit 8 distinct bank groups (conflict-free LDS.128)
+
+// ---- packed graph blob (floats), all matrices k-major W[k][N] -----------------------------------
+// (PyTorch Linear stores [out,in]; the pack kernel transposes.  w_a / Ws are used as X @ W and are
+//  already [k][N].)
+constexpr int G_WR0 = 0;                       // [9][64]
+constexpr int G_BR0 = G_WR0 + RD * HID;        // [64]
+constexpr int G_WR1 = G_BR0 + HID;             // [64][32]
+constexpr int G_BR1 = G_WR1 + HID * XD;        // [32]
+constexpr int G_WH0 = G_BR1 + XD;              // [5][64]
+constexpr int G_BH0 = G_WH0 + HD * HID;        // [64]
+constexpr int G_WH1 = G_BH0 + HID;             // [64][32]
+constexpr int G_BH1 = G_WH1 + HID * XD;        // [32]
+constexpr int G_WA  = G_BH1 + XD;              // [32][32]
+constexpr int G_WS  = G_WA + XD * XD;          // num_layer x [32][32]
+__host__ __device__ constexpr int graph_floats(int L) { return G_WS + L * XD * XD; }
+
+// ---- packed value blob: mlp(32,[32,100,100,1]); hidden 100 padded to 128 columns with zeros -----
+constexpr int VH  = RGL_VALUE_HIDDEN;   // 100
+constexpr int VHP = 128;
+constexpr int V_W0 = 0;                        // [32][32]
+constexpr int V_B0 = V_W0 + XD * XD;           // [32]
+constexpr int V_W1 = V_B0 + XD;                // [32][128]
+constexpr int V_B1 = V_W1 + XD * VHP;          // [128]
+constexpr int V_W2 = V_B1 + VHP;               // [100][128]
+constexpr int V_B2 = V_W2 + VH * VHP;          // [128]
+constexpr int V_W3 = V_B2 + VHP;               // [128]
+constexpr int V_B3 = V_W3 + VHP;               // [4] (1 used)
+constexpr int VALUE_FLOATS = V_B3 + 4;
+
+// ---- packed motion blob: mlp(32,[64,5]) ------------------------------------------------------------
+constexpr int MH = RGL_MOTION_HIDDEN;   // 64
+constexpr int M_W0 = 0;                        // [32][64] k-major
+constexpr int M_B0 = M_W0 + XD * MH;           // [64]
+constexpr int M_W1 = M_B0 + MH;                // [5][64]  (PyTorch layout: one row per output)
+constexpr int M_B1 = M_W1 + HD * MH;           // [8] (5 used)
+constexpr int MOTION_FLOATS = M_B1 + 8;
+
+static_assert(graph_floats(2) == 8256, "graph parameter count (SURVEY.md 2b)");
+static_assert(graph_floats(RGL_MAX_LAYERS) % 4 == 0 && VALUE_FLOATS % 4 == 0 && MOTION_FLOATS % 4 == 0, "16B sections");
+
+// ---- PTX: mbarrier + TMA bulk copy (cp.async.bulk -> SASS UBLKCP) ------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy, completion counted on an mbarrier (bytes % 16 == 0, both 16 B aligned)
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ float4 lds128(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void   sts128(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+// ---- warp-level register-tiled GEMM micro-kernel -------------------------------------------------
+// A warp owns a row block of RB = 8*RT rows.  lane = cg*8 + rg; thread rows = r0 + rg + 8q (q < RT),
+// thread columns = cg*4 + 16m + {0..3} (m < NC4), i.e. the warp covers 16*NC4 output columns.
+//   acc[q][4m+j] += sum_k x[row_q][k] * W[k][col]           x row-major in smem (stride ldx), K % 4 == 0
+// Shared-memory traffic per 4 k: RT LDS.128 (8 distinct rows x 16 B, conflict-free for ldx = 4 mod 32)
+// + 4*NC4 LDS.128 (4 distinct 16 B chunks, broadcast) for 16*RT*NC4 FFMA.
+template <int RT, int NC4>
+__device__ __forceinline__ void tile_gemm(float (&acc)[RT][NC4 * 4], const float* __restrict__ xrow0, int ldx,
+                                          const float* __restrict__ w, int ldw, int K) {
+    // xrow0 = &x[(r0 + rg) * ldx], w = &W[0][cg*4]
+#pragma unroll 2
+    for (int k4 = 0; k4 < K; k4 += 4) {
+        float4 xv[RT];
+#pragma unroll
+        for (int q = 0; q < RT; ++q) xv[q] = lds128(xrow0 + q * 8 * ldx + k4);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            float4 wv[NC4];
+#pragma unroll
+            for (int m = 0; m < NC4; ++m) wv[m] = lds128(w + (k4 + kk) * ldw + 16 * m);
+#pragma unroll
+            for (int q = 0; q < RT; ++q) {
+                const float xs = kk == 0 ? xv[q].x : kk == 1 ? xv[q].y : kk == 2 ? xv[q].z : xv[q].w;
+#pragma unroll
+                for (int m = 0; m < NC4; ++m) {
+                    acc[q][4 * m + 0] = fmaf(xs, wv[m].x, acc[q][4 * m + 0]);
+                    acc[q][4 * m + 1] = fmaf(xs, wv[m].y, acc[q][4 * m + 1]);
+                    acc[q][4 * m + 2] = fmaf(xs, wv[m].z, acc[q][4 * m + 2]);
+                    acc[q][4 * m + 3] = fmaf(xs, wv[m].w, acc[q][4 * m + 3]);
+                }
+            }
+        }
+    }
+}
+
+// Same tile, x read with scalar loads (tiny K not a multiple of 4: the raw 9- / 5-float states).
+template <int RT, int NC4>
+__device__ __forceinline__ void tile_gemm_smallk(float (&acc)[RT][NC4 * 4], const float* (&xrow)[RT],
+                                                 const float* __restrict__ w, int ldw, int K) {
+    for (int k = 0; k < K; ++k) {
+        float4 wv[NC4];
+#pragma unroll
+        for (int m = 0; m < NC4; ++m) wv[m] = lds128(w + k * ldw + 16 * m);
+#pragma unroll
+        for (int q = 0; q < RT; ++q) {
+            const float xs = xrow[q][k];
+#pragma unroll
+            for (int m = 0; m < NC4; ++m) {
+                acc[q][4 * m + 0] = fmaf(xs, wv[m].x, acc[q][4 * m + 0]);
+                acc[q][4 * m + 1] = fmaf(xs, wv[m].y, acc[q][4 * m + 1]);
+                acc[q][4 * m + 2] = fmaf(xs, wv[m].z, acc[q][4 * m + 2]);
+                acc[q][4 * m + 3] = fmaf(xs, wv[m].w, acc[q][4 * m + 3]);
+            }
+        }
+    }
+}
+
+}  // namespace rgl

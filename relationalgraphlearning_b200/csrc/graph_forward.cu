@@ -1,0 +1,414 @@
+// Fused RGL graph forward for sm_100a: embedding MLPs -> similarity softmax -> num_layer GCN layers
+// (-> optional state-predictor head), one launch, everything between the 136-byte input state and the
+// requested outputs stays in shared memory / registers.
+//
+// Replaces crowd_nav/policy/graph_model.py:99-130 (RGL.forward), :63-66 (embedded_gaussian similarity)
+// and the head of crowd_nav/policy/state_predictor.py:28,36.
+//
+// Work decomposition
+//   CTA      = a tile of TS states (persistent loop over tiles), weights resident in shared memory
+//              (one TMA bulk copy of the packed blob per CTA), next tile's raw states prefetched by TMA
+//              while the current tile computes.
+//   rows     = graph nodes of the tile, agent-major: row = agent*TS + state, so a 16-row block is one
+//              agent of 16 consecutive states (uniform weights, robot vs human) and the robot rows are
+//              rows [0,TS).
+//   GEMMs    = per-warp register tiles (common.cuh tile_gemm) over row-major, stride-36 smem rows.
+//   per-state= similarity row + softmax and A.H, one thread per node row, conflict-free LDS.128.
+#include "kernels.h"
+
+namespace rgl {
+
+
+template <int NCOL>
+__device__ __forceinline__ void ah_row(const float* __restrict__ AB, const float* __restrict__ XB, float* __restrict__ YB,
+                                       int r, int i, int s, int n, int TS, int c0) {
+    float acc[NCOL];
+#pragma unroll
+    for (int c = 0; c < NCOL; ++c) acc[c] = 0.f;
+    const float* arow = AB + (i * n) * TS + s;
+    for (int j = 0; j < n; ++j) {
+        const float aij = arow[j * TS];
+        const float* h = XB + (j * TS + s) * LDX + c0;
+#pragma unroll
+        for (int c4 = 0; c4 < NCOL / 4; ++c4) {
+            const float4 hv = lds128(h + 4 * c4);
+            acc[4 * c4 + 0] = fmaf(aij, hv.x, acc[4 * c4 + 0]);
+            acc[4 * c4 + 1] = fmaf(aij, hv.y, acc[4 * c4 + 1]);
+            acc[4 * c4 + 2] = fmaf(aij, hv.z, acc[4 * c4 + 2]);
+            acc[4 * c4 + 3] = fmaf(aij, hv.w, acc[4 * c4 + 3]);
+        }
+    }
+    float* y = YB + r * LDX + c0;
+#pragma unroll
+    for (int c4 = 0; c4 < NCOL / 4; ++c4)
+        sts128(y + 4 * c4, make_float4(acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]));
+}
+
+template <int TS, int RT>
+__global__ void __launch_bounds__(512, 1) graph_forward_kernel(const GraphArgs a) {
+    constexpr int RB = 8 * RT;
+    static_assert(TS % RB == 0, "a row block must not straddle two agents");
+    extern __shared__ __align__(128) float smem[];
+
+    const int n = a.Nh + 1;
+    const int R = n * TS;
+    const int nrb = R / RB;
+    const int gwf = graph_floats(a.L);
+
+    // ---- shared memory carve-up (all offsets multiples of 4 floats) ----
+    uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* bar_in = bar_w + 1;
+    float* gw = smem + 4;
+    float* mw = gw + gwf;
+    float* XB = mw + (a.mw ? MOTION_FLOATS : 0);
+    float* YB = XB + R * LDX;
+    float* AB = YB + R * LDX;
+    float* rawR = AB + n * n * TS;
+    float* rawH = rawR + TS * RD;            // TS*9 is a multiple of 4 for TS in {16,32}
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int rg = lane & 7, cg = lane >> 3;
+    const bool skip = a.flags & RGL_FLAG_SKIP, layerwise = a.flags & RGL_FLAG_LAYERWISE;
+
+    if (tid == 0) {
+        mbar_init(bar_w, 1);
+        mbar_init(bar_in, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t bytes = gwf * 4u + (a.mw ? MOTION_FLOATS * 4u : 0u);
+        mbar_arrive_expect_tx(bar_w, bytes);
+        bulk_g2s(gw, a.gw, gwf * 4u, bar_w);
+        if (a.mw) bulk_g2s(mw, a.mw, MOTION_FLOATS * 4u, bar_w);
+    }
+
+    // stage the raw states of tile t (TMA bulk copy when the tile is full and aligned, else plain loads)
+    auto load_tile = [&](int t) {
+        const int s0 = t * TS;
+        const int cnt = min(TS, a.B - s0);
+        if (a.use_tma && cnt == TS) {
+            if (tid == 0) {
+                fence_proxy_async();
+                mbar_arrive_expect_tx(bar_in, (uint32_t)(TS * RD + TS * a.Nh * HD) * 4u);
+                bulk_g2s(rawR, a.robot + (size_t)s0 * RD, TS * RD * 4u, bar_in);
+                bulk_g2s(rawH, a.humans + (size_t)s0 * a.Nh * HD, (uint32_t)(TS * a.Nh * HD) * 4u, bar_in);
+            }
+        } else {
+            for (int idx = tid; idx < TS * RD; idx += blockDim.x) {
+                const int s = idx / RD;
+                rawR[idx] = s < cnt ? __ldg(a.robot + (size_t)s0 * RD + idx) : 0.f;
+            }
+            const int hw = a.Nh * HD;
+            for (int idx = tid; idx < TS * hw; idx += blockDim.x) {
+                const int s = idx / hw, rem = idx - s * hw;
+                rawH[idx] = s < cnt ? __ldg(a.humans + (size_t)((s0 + s) / a.hb) * hw + rem) : 0.f;
+            }
+        }
+    };
+
+    uint32_t in_parity = 0;
+    if ((int)blockIdx.x < a.ntiles) load_tile(blockIdx.x);
+    mbar_wait(bar_w, 0);
+
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        const int s0 = tile * TS;
+        const int cnt = min(TS, a.B - s0);
+        if (a.use_tma && cnt == TS) {
+            mbar_wait(bar_in, in_parity);
+            in_parity ^= 1;
+        }
+        __syncthreads();
+
+        // ================= embedding: X = relu(W1 relu(W0 x + b0) + b1); Y = X w_a =================
+        for (int rb = warp; rb < nrb; rb += nwarps) {
+            const int r0 = rb * RB;
+            const int agent = r0 / TS;
+            const int sb = r0 - agent * TS;
+            const float *W0, *B0, *W1, *B1;
+            int K0;
+            const float* xrow[RT];
+            if (agent == 0) {
+                W0 = gw + G_WR0; B0 = gw + G_BR0; W1 = gw + G_WR1; B1 = gw + G_BR1; K0 = RD;
+#pragma unroll
+                for (int q = 0; q < RT; ++q) xrow[q] = rawR + (sb + rg + 8 * q) * RD;
+            } else {
+                W0 = gw + G_WH0; B0 = gw + G_BH0; W1 = gw + G_WH1; B1 = gw + G_BH1; K0 = HD;
+#pragma unroll
+                for (int q = 0; q < RT; ++q) xrow[q] = rawH + ((sb + rg + 8 * q) * a.Nh + (agent - 1)) * HD;
+            }
+            float acc2[RT][8];
+#pragma unroll
+            for (int q = 0; q < RT; ++q)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) acc2[q][c] = 0.f;
+            float* scr = YB + (r0 + rg) * LDX;       // this warp's own rows of YB double as the hidden scratch
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                float acc1[RT][8];
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    const float4 b = lds128(B0 + half * 32 + cg * 4 + 16 * m);
+#pragma unroll
+                    for (int q = 0; q < RT; ++q) {
+                        acc1[q][4 * m + 0] = b.x; acc1[q][4 * m + 1] = b.y; acc1[q][4 * m + 2] = b.z; acc1[q][4 * m + 3] = b.w;
+                    }
+                }
+                tile_gemm_smallk<RT, 2>(acc1, xrow, W0 + half * 32 + cg * 4, HID, K0);
+#pragma unroll
+                for (int q = 0; q < RT; ++q)
+#pragma unroll
+                    for (int m = 0; m < 2; ++m)
+                        sts128(scr + q * 8 * LDX + cg * 4 + 16 * m,
+                               make_float4(fmaxf(acc1[q][4 * m], 0.f), fmaxf(acc1[q][4 * m + 1], 0.f),
+                                           fmaxf(acc1[q][4 * m + 2], 0.f), fmaxf(acc1[q][4 * m + 3], 0.f)));
+                __syncwarp();
+                tile_gemm<RT, 2>(acc2, scr, LDX, W1 + half * 32 * XD + cg * 4, XD, 32);
+                __syncwarp();
+            }
+            float* xo = XB + (r0 + rg) * LDX;
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                const float4 b = lds128(B1 + cg * 4 + 16 * m);
+#pragma unroll
+                for (int q = 0; q < RT; ++q)
+                    sts128(xo + q * 8 * LDX + cg * 4 + 16 * m,
+                           make_float4(fmaxf(acc2[q][4 * m] + b.x, 0.f), fmaxf(acc2[q][4 * m + 1] + b.y, 0.f),
+                                       fmaxf(acc2[q][4 * m + 2] + b.z, 0.f), fmaxf(acc2[q][4 * m + 3] + b.w, 0.f)));
+            }
+            __syncwarp();
+            float accy[RT][8];
+#pragma unroll
+            for (int q = 0; q < RT; ++q)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) accy[q][c] = 0.f;
+            tile_gemm<RT, 2>(accy, xo, LDX, gw + G_WA + cg * 4, XD, XD);
+#pragma unroll
+            for (int q = 0; q < RT; ++q)
+#pragma unroll
+                for (int m = 0; m < 2; ++m)
+                    sts128(scr + q * 8 * LDX + cg * 4 + 16 * m,
+                           make_float4(accy[q][4 * m], accy[q][4 * m + 1], accy[q][4 * m + 2], accy[q][4 * m + 3]));
+        }
+        __syncthreads();
+
+        // raw inputs are dead: prefetch the next tile's states under this tile's GCN layers
+        if (tile + (int)gridDim.x < a.ntiles) load_tile(tile + gridDim.x);
+
+        // ================= GCN layers =================
+        for (int l = 0; l < a.L; ++l) {
+            const bool last = (l == a.L - 1);
+            const bool robot_only = last && a.H == nullptr && a.S == nullptr;
+            const int rows = robot_only ? TS : R;        // node rows that must be produced by this layer
+
+            if (l == 0 || layerwise) {
+                if (l > 0) {                              // Y = H w_a for the layerwise graph
+                    for (int rb = warp; rb * RB < rows; rb += nwarps) {
+                        const int r0 = rb * RB;
+                        float accy[RT][8];
+#pragma unroll
+                        for (int q = 0; q < RT; ++q)
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) accy[q][c] = 0.f;
+                        tile_gemm<RT, 2>(accy, XB + (r0 + rg) * LDX, LDX, gw + G_WA + cg * 4, XD, XD);
+                        float* yo = YB + (r0 + rg) * LDX;
+#pragma unroll
+                        for (int q = 0; q < RT; ++q)
+#pragma unroll
+                            for (int m = 0; m < 2; ++m)
+                                sts128(yo + q * 8 * LDX + cg * 4 + 16 * m,
+                                       make_float4(accy[q][4 * m], accy[q][4 * m + 1], accy[q][4 * m + 2], accy[q][4 * m + 3]));
+                    }
+                    __syncthreads();
+                }
+                // ---- similarity row + softmax: A[i][:] = softmax_j( Y[i] . X[j] ) ----
+                for (int r = warp * 32 + lane; r < rows; r += nwarps * 32) {
+                    const int i = r / TS, s = r - i * TS;
+                    float4 y[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) y[c] = lds128(YB + r * LDX + 4 * c);
+                    float* arow = AB + (i * n) * TS + s;
+                    float mx = -INFINITY;
+                    for (int j = 0; j < n; ++j) {
+                        const float* x = XB + (j * TS + s) * LDX;
+                        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const float4 xv = lds128(x + 4 * c);
+                            d0 = fmaf(y[c].x, xv.x, d0); d1 = fmaf(y[c].y, xv.y, d1);
+                            d2 = fmaf(y[c].z, xv.z, d2); d3 = fmaf(y[c].w, xv.w, d3);
+                        }
+                        const float d = (d0 + d1) + (d2 + d3);
+                        arow[j * TS] = d;
+                        mx = fmaxf(mx, d);
+                    }
+                    float sum = 0.f;
+                    for (int j = 0; j < n; ++j) {
+                        const float e = expf(arow[j * TS] - mx);
+                        arow[j * TS] = e;
+                        sum += e;
+                    }
+                    const bool writeA0 = a.A0 != nullptr && l == 0 && (s0 + s) == 0;
+                    for (int j = 0; j < n; ++j) {
+                        const float p = arow[j * TS] / sum;
+                        arow[j * TS] = p;
+                        if (writeA0) a.A0[i * n + j] = p;
+                    }
+                }
+                __syncthreads();
+            }
+
+            // ---- AH = A . H  (per state; one thread per node row, optionally split in two column halves) ----
+            {
+                const int chunks = (rows + 31) / 32;
+                if (chunks >= nwarps) {
+                    for (int r = warp * 32 + lane; r < rows; r += nwarps * 32) {
+                        const int i = r / TS;
+                        ah_row<32>(AB, XB, YB, r, i, r - i * TS, n, TS, 0);
+                    }
+                } else {
+                    for (int it = warp; it < chunks * 2; it += nwarps) {
+                        const int r = (it >> 1) * 32 + lane;
+                        if (r < rows) {
+                            const int i = r / TS;
+                            ah_row<16>(AB, XB, YB, r, i, r - i * TS, n, TS, (it & 1) * 16);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+
+            // ---- H' = relu(AH . W_l) (+ H), in place over XB; last layer streams the outputs to HBM ----
+            for (int rb = warp; rb * RB < rows; rb += nwarps) {
+                const int r0 = rb * RB;
+                const int agent = r0 / TS;
+                float acc[RT][8];
+#pragma unroll
+                for (int q = 0; q < RT; ++q)
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) acc[q][c] = 0.f;
+                tile_gemm<RT, 2>(acc, YB + (r0 + rg) * LDX, LDX, gw + G_WS + l * XD * XD + cg * 4, XD, XD);
+                float* xo = XB + (r0 + rg) * LDX;
+#pragma unroll
+                for (int q = 0; q < RT; ++q) {
+                    const int s = r0 + rg + 8 * q - agent * TS;
+#pragma unroll
+                    for (int m = 0; m < 2; ++m) {
+                        float4 v = make_float4(fmaxf(acc[q][4 * m], 0.f), fmaxf(acc[q][4 * m + 1], 0.f),
+                                               fmaxf(acc[q][4 * m + 2], 0.f), fmaxf(acc[q][4 * m + 3], 0.f));
+                        float* p = xo + q * 8 * LDX + cg * 4 + 16 * m;
+                        if (skip) {
+                            const float4 h = lds128(p);
+                            v.x += h.x; v.y += h.y; v.z += h.z; v.w += h.w;
+                        }
+                        sts128(p, v);
+                        if (last && s < cnt) {
+                            const size_t gs = (size_t)(s0 + s);
+                            if (a.H) *reinterpret_cast<float4*>(a.H + (gs * n + agent) * XD + cg * 4 + 16 * m) = v;
+                            if (a.E && agent == 0) *reinterpret_cast<float4*>(a.E + gs * XD + cg * 4 + 16 * m) = v;
+                        }
+                    }
+                }
+                // ---- state-predictor head on human rows: S = W1 relu(W0 h + b0) + b1 (32 -> 64 -> 5) ----
+                if (last && a.S != nullptr && agent >= 1) {
+                    __syncwarp();
+                    constexpr int LPR = 32 / RB;          // lanes per row in the 64->5 dot (2 for RB=16, 1 for RB=32)
+                    constexpr int KPL = 32 / LPR;         // k per lane per half
+                    const int rl = lane % RB, kh = lane / RB;
+                    float part[HD];
+#pragma unroll
+                    for (int c = 0; c < HD; ++c) part[c] = 0.f;
+                    float* scr = YB + (r0 + rg) * LDX;
+#pragma unroll 1
+                    for (int half = 0; half < 2; ++half) {
+                        float acc1[RT][8];
+#pragma unroll
+                        for (int m = 0; m < 2; ++m) {
+                            const float4 b = lds128(mw + M_B0 + half * 32 + cg * 4 + 16 * m);
+#pragma unroll
+                            for (int q = 0; q < RT; ++q) {
+                                acc1[q][4 * m + 0] = b.x; acc1[q][4 * m + 1] = b.y; acc1[q][4 * m + 2] = b.z; acc1[q][4 * m + 3] = b.w;
+                            }
+                        }
+                        tile_gemm<RT, 2>(acc1, xo, LDX, mw + M_W0 + half * 32 + cg * 4, MH, XD);
+#pragma unroll
+                        for (int q = 0; q < RT; ++q)
+#pragma unroll
+                            for (int m = 0; m < 2; ++m)
+                                sts128(scr + q * 8 * LDX + cg * 4 + 16 * m,
+                                       make_float4(fmaxf(acc1[q][4 * m], 0.f), fmaxf(acc1[q][4 * m + 1], 0.f),
+                                                   fmaxf(acc1[q][4 * m + 2], 0.f), fmaxf(acc1[q][4 * m + 3], 0.f)));
+                        __syncwarp();
+                        const float* hrow = YB + (r0 + rl) * LDX + kh * KPL;
+#pragma unroll
+                        for (int k4 = 0; k4 < KPL / 4; ++k4) {
+                            const float4 hv = lds128(hrow + 4 * k4);
+#pragma unroll
+                            for (int c = 0; c < HD; ++c) {
+                                const float4 wv = lds128(mw + M_W1 + c * MH + half * 32 + kh * KPL + 4 * k4);
+                                part[c] = fmaf(hv.x, wv.x, part[c]); part[c] = fmaf(hv.y, wv.y, part[c]);
+                                part[c] = fmaf(hv.z, wv.z, part[c]); part[c] = fmaf(hv.w, wv.w, part[c]);
+                            }
+                        }
+                        __syncwarp();
+                    }
+                    if (LPR == 2) {
+#pragma unroll
+                        for (int c = 0; c < HD; ++c) part[c] += __shfl_xor_sync(0xffffffffu, part[c], 16);
+                    }
+                    const int s = r0 + rl - agent * TS;
+                    if (kh == 0 && s < cnt) {
+                        float* so = a.S + ((size_t)(s0 + s) * a.Nh + (agent - 1)) * HD;
+#pragma unroll
+                        for (int c = 0; c < HD; ++c) so[c] = part[c] + mw[M_B1 + c];
+                    }
+                }
+            }
+            if (!last) __syncthreads();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+size_t graph_smem_bytes(int TS, int Nh, int L, bool motion) {
+    const int n = Nh + 1;
+    size_t fl = 4 + graph_floats(L) + (motion ? MOTION_FLOATS : 0) + 2 * (size_t)n * TS * LDX + (size_t)n * n * TS +
+                TS * RD + ((TS * Nh * HD + 3) & ~3);
+    return fl * sizeof(float);
+}
+
+template <int TS, int RT>
+static cudaError_t launch_graph(const GraphArgs& a, int num_sms, size_t max_smem, cudaStream_t st) {
+    const int n = a.Nh + 1;
+    const size_t smem = graph_smem_bytes(TS, a.Nh, a.L, a.mw != nullptr);
+    if (smem > max_smem) return cudaErrorInvalidConfiguration;
+    GraphArgs b = a;
+    b.ntiles = (a.B + TS - 1) / TS;
+    const int nrb = n * TS / (8 * RT);
+    const int nwarps = nrb < 16 ? nrb : 16;
+    static bool attr_set = false;     // benign race: idempotent
+    cudaError_t e = cudaSuccess;
+    if (!attr_set) {
+        e = cudaFuncSetAttribute(graph_forward_kernel<TS, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    int per_sm = (int)((228 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    const int max_thr = 2048 / (nwarps * 32);
+    if (per_sm > max_thr) per_sm = max_thr;
+    int grid = b.ntiles < num_sms * per_sm ? b.ntiles : num_sms * per_sm;
+    graph_forward_kernel<TS, RT><<<grid, nwarps * 32, smem, st>>>(b);
+    return cudaGetLastError();
+}
+
+cudaError_t run_graph_forward(const GraphArgs& a, int num_sms, size_t max_smem, cudaStream_t st) {
+    // pick the largest state tile that fits in shared memory; small batches prefer more CTAs
+    const bool fits32 = graph_smem_bytes(32, a.Nh, a.L, a.mw != nullptr) <= max_smem;
+    const int tiles32 = (a.B + 31) / 32;
+    if (fits32 && tiles32 >= num_sms / 2) return launch_graph<32, 2>(a, num_sms, max_smem, st);
+    if (graph_smem_bytes(16, a.Nh, a.L, a.mw != nullptr) <= max_smem) return launch_graph<16, 2>(a, num_sms, max_smem, st);
+    return cudaErrorInvalidConfiguration;
+}
+
+}  // namespace rgl

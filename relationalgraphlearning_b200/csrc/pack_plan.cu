@@ -1,0 +1,154 @@
+// Small helper kernels: weight packing (PyTorch state_dict layout -> k-major blobs) and the batched
+// look-ahead step of the planner (next robot state + reward estimate + first-max argmax).
+#include "kernels.h"
+
+namespace rgl {
+
+// dst[k*Np + o] = w[o*K + k] for o < N (PyTorch Linear weight [N,K]); columns N..Np-1 are zero-filled.
+__device__ __forceinline__ void pack_linear_T(float* dst, const float* w, int N, int K, int Np, int t, int nt) {
+    for (int idx = t; idx < K * Np; idx += nt) {
+        const int k = idx / Np, o = idx - k * Np;
+        dst[idx] = o < N ? w[o * K + k] : 0.f;
+    }
+}
+__device__ __forceinline__ void pack_copy(float* dst, const float* src, int N, int Np, int t, int nt) {
+    for (int idx = t; idx < Np; idx += nt) dst[idx] = idx < N ? src[idx] : 0.f;
+}
+
+__global__ void pack_graph_kernel(RglGraphParams p, float* out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    pack_linear_T(out + G_WR0, p.wr0_w, HID, RD, HID, t, nt);
+    pack_copy(out + G_BR0, p.wr0_b, HID, HID, t, nt);
+    pack_linear_T(out + G_WR1, p.wr1_w, XD, HID, XD, t, nt);
+    pack_copy(out + G_BR1, p.wr1_b, XD, XD, t, nt);
+    pack_linear_T(out + G_WH0, p.wh0_w, HID, HD, HID, t, nt);
+    pack_copy(out + G_BH0, p.wh0_b, HID, HID, t, nt);
+    pack_linear_T(out + G_WH1, p.wh1_w, XD, HID, XD, t, nt);
+    pack_copy(out + G_BH1, p.wh1_b, XD, XD, t, nt);
+    pack_copy(out + G_WA, p.w_a, XD * XD, XD * XD, t, nt);
+    for (int l = 0; l < p.num_layer; ++l) pack_copy(out + G_WS + l * XD * XD, p.Ws[l], XD * XD, XD * XD, t, nt);
+}
+
+__global__ void pack_value_kernel(RglValueParams p, float* out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    pack_linear_T(out + V_W0, p.w0, XD, XD, XD, t, nt);
+    pack_copy(out + V_B0, p.b0, XD, XD, t, nt);
+    pack_linear_T(out + V_W1, p.w1, VH, XD, VHP, t, nt);
+    pack_copy(out + V_B1, p.b1, VH, VHP, t, nt);
+    pack_linear_T(out + V_W2, p.w2, VH, VH, VHP, t, nt);
+    pack_copy(out + V_B2, p.b2, VH, VHP, t, nt);
+    pack_copy(out + V_W3, p.w3, VH, VHP, t, nt);
+    pack_copy(out + V_B3, p.b3, 1, 4, t, nt);
+}
+
+__global__ void pack_motion_kernel(RglMotionParams p, float* out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    pack_linear_T(out + M_W0, p.w0, MH, XD, MH, t, nt);
+    pack_copy(out + M_B0, p.b0, MH, MH, t, nt);
+    pack_copy(out + M_W1, p.w1, HD * MH, HD * MH, t, nt);
+    pack_copy(out + M_B1, p.b1, HD, 8, t, nt);
+}
+
+// ---- planner: one thread per (state e, action a) ------------------------------------------------------
+// next robot state: crowd_nav/policy/state_predictor.py:48-52 (fp32 position + fp32(v*dt), velocity = action)
+// reward:           crowd_nav/policy/model_predictive_rl.py:304-357, crowd_sim/envs/utils/utils.py:4-26, in float64
+__global__ void plan_expand_kernel(const float* __restrict__ robot, const float* __restrict__ humans, int E, int Nh,
+                                   const double* __restrict__ actions, int A, double dt,
+                                   float* __restrict__ next_robot, float* __restrict__ reward) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= E * A) return;
+    const int e = idx / A, a = idx - e * A;
+    const float* r = robot + (size_t)e * RD;
+    const double avx = actions[2 * a], avy = actions[2 * a + 1];
+    if (next_robot) {
+        float* o = next_robot + (size_t)idx * RD;
+        o[0] = __fadd_rn(r[0], (float)(avx * dt));
+        o[1] = __fadd_rn(r[1], (float)(avy * dt));
+        o[2] = (float)avx;
+        o[3] = (float)avy;
+#pragma unroll
+        for (int c = 4; c < RD; ++c) o[c] = r[c];
+    }
+    if (reward) {
+        const double rpx = r[0], rpy = r[1], rrad = r[4], gx = r[5], gy = r[6];
+        double dmin = INFINITY;
+        bool collision = false;
+        const float* h = humans + (size_t)e * Nh * HD;
+        for (int j = 0; j < Nh; ++j, h += HD) {
+            const double px = (double)h[0] - rpx, py = (double)h[1] - rpy;
+            const double vx = (double)h[2] - avx, vy = (double)h[3] - avy;
+            const double ex = __dadd_rn(px, __dmul_rn(vx, dt)), ey = __dadd_rn(py, __dmul_rn(vy, dt));
+            // distance from the origin to the segment (px,py)-(ex,ey)
+            const double sx = ex - px, sy = ey - py;
+            double d;
+            if (sx == 0.0 && sy == 0.0) {
+                d = sqrt(__dadd_rn(__dmul_rn(px, px), __dmul_rn(py, py)));
+            } else {
+                double u = __dadd_rn(__dmul_rn(-px, sx), __dmul_rn(-py, sy)) / __dadd_rn(__dmul_rn(sx, sx), __dmul_rn(sy, sy));
+                u = u > 1.0 ? 1.0 : (u < 0.0 ? 0.0 : u);
+                const double x = __dadd_rn(px, __dmul_rn(u, sx)), y = __dadd_rn(py, __dmul_rn(u, sy));
+                d = sqrt(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)));
+            }
+            d = d - (double)h[4] - rrad;
+            if (d < 0.0) { collision = true; break; }
+            if (d < dmin) dmin = d;
+        }
+        const double qx = __dadd_rn(rpx, __dmul_rn(avx, dt)) - gx, qy = __dadd_rn(rpy, __dmul_rn(avy, dt)) - gy;
+        const bool reaching = sqrt(__dadd_rn(__dmul_rn(qx, qx), __dmul_rn(qy, qy))) < rrad;
+        double rew;
+        if (collision) rew = -0.25;
+        else if (reaching) rew = 1.0;
+        else if (dmin < 0.2) rew = __dmul_rn(__dmul_rn(dmin - 0.2, 0.5), dt);
+        else rew = 0.0;
+        reward[idx] = (float)rew;
+    }
+}
+
+// value = fp32(reward) + fp32(gamma_bar) * V (two rounded fp32 ops, like the tensor expression in
+// model_predictive_rl.py:227); best = first index of the maximum under a strict '>' scan (:228-231).
+__global__ void plan_argmax_kernel(const float* __restrict__ reward, const float* __restrict__ V, int E, int A, float gamma_bar,
+                                   float* __restrict__ value, int* __restrict__ best) {
+    const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (e >= E) return;
+    float bv = -INFINITY;
+    int bi = -1;
+    for (int a = lane; a < A; a += 32) {
+        const float v = __fadd_rn(reward[(size_t)e * A + a], __fmul_rn(gamma_bar, V[(size_t)e * A + a]));
+        if (value) value[(size_t)e * A + a] = v;
+        if (v > bv) { bv = v; bi = a; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+        if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+    }
+    if (lane == 0 && best) best[e] = bi;
+}
+
+cudaError_t run_pack_graph(const RglGraphParams& p, float* out, cudaStream_t st) {
+    pack_graph_kernel<<<8, 256, 0, st>>>(p, out);
+    return cudaGetLastError();
+}
+cudaError_t run_pack_value(const RglValueParams& p, float* out, cudaStream_t st) {
+    pack_value_kernel<<<16, 256, 0, st>>>(p, out);
+    return cudaGetLastError();
+}
+cudaError_t run_pack_motion(const RglMotionParams& p, float* out, cudaStream_t st) {
+    pack_motion_kernel<<<4, 256, 0, st>>>(p, out);
+    return cudaGetLastError();
+}
+cudaError_t run_plan_expand(const float* robot, const float* humans, int E, int Nh, const double* actions, int A, double dt,
+                            float* next_robot, float* reward, cudaStream_t st) {
+    const int total = E * A;
+    plan_expand_kernel<<<(total + 127) / 128, 128, 0, st>>>(robot, humans, E, Nh, actions, A, dt, next_robot, reward);
+    return cudaGetLastError();
+}
+cudaError_t run_plan_argmax(const float* reward, const float* V, int E, int A, float gamma_bar, float* value, int* best,
+                            cudaStream_t st) {
+    plan_argmax_kernel<<<(E + 3) / 4, 128, 0, st>>>(reward, V, E, A, gamma_bar, value, best);
+    return cudaGetLastError();
+}
+
+}  // namespace rgl

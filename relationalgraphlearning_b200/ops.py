@@ -1,0 +1,244 @@
+"""Tensor-level wrappers over the C ABI (include/rgl_b200.h): packing caches, forward ops, autograd glue.
+
+Every function here launches hand-written sm_100a kernels through ctypes on the current CUDA stream of
+the inputs' device.  There is no alternative compute path for CUDA tensors: if librgl_b200.so is missing
+or a call fails an exception propagates.
+"""
+import ctypes
+import weakref
+
+import torch
+
+from . import _lib
+from . import _torch_math as TM
+
+LAUNCHES = 0        # kernels launched through this module (bench.py reports it as gpu_launches)
+
+
+def _count(n):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ---------------------------------------------------------------- weight packing ----------------
+class _PackCache(object):
+    """Packed k-major blob of one module, rebuilt when any parameter changed.
+
+    Change detection = (data_ptr, _version) of every parameter: optimizers, load_state_dict and
+    .to(device) all bump one of the two.  Writes through `.data` do not; call mark_dirty() then.
+    """
+
+    def __init__(self):
+        self.key = None
+        self.blob = None
+
+    def mark_dirty(self):
+        self.key = None
+
+    def get(self, params, nfloats, pack_fn):
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if key != self.key or self.blob is None or self.blob.device != params[0].device:
+            dev = params[0].device
+            if self.blob is None or self.blob.device != dev or self.blob.numel() != nfloats:
+                self.blob = torch.empty(nfloats, dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                pack_fn(self.blob)
+            _count(1)
+            self.key = key
+        return self.blob
+
+
+def _graph_param_list(rgl):
+    return [rgl.w_r[0].weight, rgl.w_r[0].bias, rgl.w_r[2].weight, rgl.w_r[2].bias,
+            rgl.w_h[0].weight, rgl.w_h[0].bias, rgl.w_h[2].weight, rgl.w_h[2].bias, rgl.w_a] + list(rgl.Ws)
+
+
+def packed_graph(rgl):
+    params = [p.detach() for p in _graph_param_list(rgl)]
+    L = len(rgl.Ws)
+    lib = _lib.lib()
+
+    def pack(blob):
+        gp = _lib.GraphParams()
+        names = ['wr0_w', 'wr0_b', 'wr1_w', 'wr1_b', 'wh0_w', 'wh0_b', 'wh1_w', 'wh1_b', 'w_a']
+        keep = [_f32c(p) for p in params]
+        for nme, t in zip(names, keep[:9]):
+            setattr(gp, nme, t.data_ptr())
+        for i in range(L):
+            gp.Ws[i] = keep[9 + i].data_ptr()
+        gp.num_layer = L
+        _lib.check(lib.rgl_pack_graph(ctypes.byref(gp), _lib.ptr(blob), _lib.stream_ptr(blob.device)), 'rgl_pack_graph')
+
+    return rgl._pack_cache.get(params, int(lib.rgl_packed_graph_floats(L)), pack)
+
+
+def packed_value(seq, cache):
+    params = [seq[0].weight, seq[0].bias, seq[2].weight, seq[2].bias, seq[4].weight, seq[4].bias,
+              seq[6].weight, seq[6].bias]
+    params = [p.detach() for p in params]
+    lib = _lib.lib()
+
+    def pack(blob):
+        vp = _lib.ValueParams()
+        keep = [_f32c(p) for p in params]
+        for nme, t in zip(['w0', 'b0', 'w1', 'b1', 'w2', 'b2', 'w3', 'b3'], keep):
+            setattr(vp, nme, t.data_ptr())
+        _lib.check(lib.rgl_pack_value(ctypes.byref(vp), _lib.ptr(blob), _lib.stream_ptr(blob.device)), 'rgl_pack_value')
+
+    return cache.get(params, int(lib.rgl_packed_value_floats()), pack)
+
+
+def packed_motion(seq, cache):
+    params = [p.detach() for p in (seq[0].weight, seq[0].bias, seq[2].weight, seq[2].bias)]
+    lib = _lib.lib()
+
+    def pack(blob):
+        mp = _lib.MotionParams()
+        keep = [_f32c(p) for p in params]
+        for nme, t in zip(['w0', 'b0', 'w1', 'b1'], keep):
+            setattr(mp, nme, t.data_ptr())
+        _lib.check(lib.rgl_pack_motion(ctypes.byref(mp), _lib.ptr(blob), _lib.stream_ptr(blob.device)), 'rgl_pack_motion')
+
+    return cache.get(params, int(lib.rgl_packed_motion_floats()), pack)
+
+
+# ---------------------------------------------------------------- raw forward ops ----------------
+def _check_state(robot, humans):
+    if not (robot.is_cuda and humans.is_cuda):
+        raise _lib.RglError('relationalgraphlearning_b200 computes on CUDA devices only: move the module and its '
+                            'inputs to a CUDA device (there is no CPU path)')
+    assert robot.dim() == 3 and humans.dim() == 3 and robot.size(1) == 1 and robot.size(2) == 9 and humans.size(2) == 5
+    return _f32c(robot), _f32c(humans)
+
+
+def graph_forward_raw(gblob, num_layer, flags, robot, humans, humans_bcast=1, mblob=None,
+                      want_H=False, want_E=False, want_S=False, want_A0=False):
+    """One launch of the fused graph kernel.  Returns dict with the requested outputs."""
+    robot, humans = _check_state(robot, humans)
+    B, Nh = robot.size(0), humans.size(1)
+    assert humans.size(0) * humans_bcast >= B
+    n = Nh + 1
+    dev = robot.device
+    out = {}
+    if want_H:
+        out['H'] = torch.empty(B, n, 32, dtype=torch.float32, device=dev)
+    if want_E:
+        out['E'] = torch.empty(B, 32, dtype=torch.float32, device=dev)
+    if want_S:
+        out['S'] = torch.empty(B, Nh, 5, dtype=torch.float32, device=dev)
+    if want_A0:
+        out['A0'] = torch.empty(n, n, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.lib().rgl_graph_forward(_lib.ptr(robot), _lib.ptr(humans), B, Nh, humans_bcast, _lib.ptr(gblob),
+                                          num_layer, flags, _lib.ptr(mblob) if want_S else None,
+                                          _lib.ptr(out.get('H')), _lib.ptr(out.get('E')), _lib.ptr(out.get('S')),
+                                          _lib.ptr(out.get('A0')), _lib.stream_ptr(dev))
+    _lib.check(rc, 'rgl_graph_forward')
+    _count(1 if B > 0 else 0)
+    return out
+
+
+def value_head_raw(vblob, E):
+    E = _f32c(E)
+    B = E.size(0)
+    V = torch.empty(B, 1, dtype=torch.float32, device=E.device)
+    with torch.cuda.device(E.device):
+        rc = _lib.lib().rgl_value_head(_lib.ptr(E), B, _lib.ptr(vblob), _lib.ptr(V), _lib.stream_ptr(E.device))
+    _lib.check(rc, 'rgl_value_head')
+    _count(1 if B > 0 else 0)
+    return V
+
+
+def gcn_layer(X, W, A=None, w_a=None, skip=False, return_A=False):
+    """Hout = relu((A X) W) (+X); A given [B,n,n] or computed as softmax(X w_a X^T)."""
+    X = _f32c(X)
+    B, n, _ = X.shape
+    Hout = torch.empty_like(X)
+    Aout = torch.empty(B, n, n, dtype=torch.float32, device=X.device) if return_A else None
+    with torch.cuda.device(X.device):
+        rc = _lib.lib().rgl_gcn_layer(_lib.ptr(X), _lib.ptr(_f32c(A)) if A is not None else None, _lib.ptr(_f32c(W)),
+                                      _lib.ptr(_f32c(w_a)) if w_a is not None else None, B, n,
+                                      _lib.FLAG_SKIP if skip else 0, _lib.ptr(Hout), _lib.ptr(Aout), _lib.stream_ptr(X.device))
+    _lib.check(rc, 'rgl_gcn_layer')
+    _count(1 if B > 0 else 0)
+    return (Hout, Aout) if return_A else Hout
+
+
+def plan_expand(robot, humans, actions, time_step, want_next=True, want_reward=True):
+    """robot[E,1,9], humans[E,Nh,5], actions double[A,2] -> next_robot[E*A,1,9], reward[E*A]."""
+    robot, humans = _check_state(robot, humans)
+    E, Nh, A = robot.size(0), humans.size(1), actions.size(0)
+    assert actions.dtype == torch.float64 and actions.is_cuda and actions.is_contiguous()
+    nxt = torch.empty(E * A, 1, 9, dtype=torch.float32, device=robot.device) if want_next else None
+    rew = torch.empty(E * A, dtype=torch.float32, device=robot.device) if want_reward else None
+    with torch.cuda.device(robot.device):
+        rc = _lib.lib().rgl_plan_expand(_lib.ptr(robot), _lib.ptr(humans), E, Nh, _lib.ptr(actions), A, float(time_step),
+                                        _lib.ptr(nxt), _lib.ptr(rew), _lib.stream_ptr(robot.device))
+    _lib.check(rc, 'rgl_plan_expand')
+    _count(1 if E > 0 else 0)
+    return nxt, rew
+
+
+def plan_argmax(reward, V, E, A, gamma_bar, want_value=True):
+    reward, V = _f32c(reward), _f32c(V)
+    value = torch.empty(E, A, dtype=torch.float32, device=V.device) if want_value else None
+    best = torch.empty(E, dtype=torch.int32, device=V.device)
+    with torch.cuda.device(V.device):
+        rc = _lib.lib().rgl_plan_argmax(_lib.ptr(reward), _lib.ptr(V), E, A, float(gamma_bar), _lib.ptr(value),
+                                        _lib.ptr(best), _lib.stream_ptr(V.device))
+    _lib.check(rc, 'rgl_plan_argmax')
+    _count(1 if E > 0 else 0)
+    return value, best
+
+
+# ---------------------------------------------------------------- autograd glue -------------------
+def _needs_grad(*tensors_or_modules):
+    if not torch.is_grad_enabled():
+        return False
+    for t in tensors_or_modules:
+        if isinstance(t, torch.Tensor):
+            if t.requires_grad:
+                return True
+        else:
+            for p in t.parameters():
+                if p.requires_grad:
+                    return True
+    return False
+
+
+class _FusedForward(torch.autograd.Function):
+    """Forward = sm_100a kernels; backward = autograd recompute with torch ops on the same GPU
+    (placeholder until the fused backward kernels land; see _torch_math.py)."""
+
+    @staticmethod
+    def forward(ctx, run_kernels, run_torch, nparams, *tensors):
+        ctx.run_torch = run_torch
+        ctx.nparams = nparams
+        ctx.save_for_backward(*tensors)
+        return run_kernels()
+
+    @staticmethod
+    def backward(ctx, *grad_outs):
+        tensors = ctx.saved_tensors
+        with torch.enable_grad():
+            outs = ctx.run_torch()
+            if isinstance(outs, torch.Tensor):
+                outs = (outs,)
+            wanted = [t for t, need in zip(tensors, ctx.needs_input_grad[3:]) if need]
+            grads = torch.autograd.grad(outs, wanted, grad_outs, allow_unused=True)
+        it = iter(grads)
+        res = [next(it) if need else None for need in ctx.needs_input_grad[3:]]
+        return (None, None, None) + tuple(res)
+
+
+def fused_with_autograd(run_kernels, run_torch, params, inputs):
+    """run_kernels(): no-grad CUDA kernel path; run_torch(): differentiable torch restatement over the SAME
+    parameter / input tensors (they are passed to the Function so autograd routes the gradients)."""
+    tensors = list(params) + list(inputs)
+    return _FusedForward.apply(run_kernels, run_torch, len(params), *tensors)

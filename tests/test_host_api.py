@@ -1,0 +1,112 @@
+"""CPU-side checks (-m "not gpu"): module API / checkpoint compatibility with the reference, C-ABI exports."""
+import copy
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+from relationalgraphlearning_b200 import _lib
+from relationalgraphlearning_b200.config import policy_config
+from relationalgraphlearning_b200.graph_model import RGL
+from relationalgraphlearning_b200.state_predictor import LinearStatePredictor, StatePredictor, compute_next_robot_state
+from relationalgraphlearning_b200.value_estimator import ValueEstimator
+
+
+def build(seed=0, **kw):
+    cfg = policy_config(**kw)
+    torch.manual_seed(seed)
+    g1 = RGL(cfg, 9, 5)
+    ve = ValueEstimator(cfg, g1)
+    g2 = RGL(cfg, 9, 5)
+    sp = StatePredictor(cfg, g2, 0.25)
+    return cfg, g1, ve, g2, sp
+
+
+def test_library_exports_every_declared_symbol():
+    """Every function declared in include/rgl_b200.h is exported by librgl_b200.so (no compute calls here)."""
+    hdr = open(os.path.join(ROOT, 'include', 'rgl_b200.h')).read()
+    declared = set(re.findall(r'\b(rgl_[a-z_0-9]+)\s*\(', hdr))
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(handle, name), name
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    lib = _lib.lib()
+    assert lib.rgl_version() == 100
+    assert lib.rgl_packed_graph_floats(2) == 8256       # SURVEY.md 2b parameter inventory
+    assert lib.rgl_packed_graph_floats(0) == 0 and lib.rgl_packed_graph_floats(5) == 0
+
+
+def test_argument_validation_without_gpu():
+    lib = _lib.lib()
+    rc = lib.rgl_graph_forward(None, None, 4, 5, 1, None, 2, 1, None, None, None, None, None, None)
+    assert rc == -1 and b'null' in lib.rgl_last_error_string()
+    rc = lib.rgl_value_head(None, 4, None, None, None)
+    assert rc == -1
+
+
+@pytest.mark.parametrize('seed', [0, 1, 2])
+def test_same_seed_same_weights_as_reference(seed):
+    """Parameter names, shapes and creation order match the reference: torch.manual_seed(s) reproduces the
+    exact tensors the reference modules were initialised with (golden fixtures hold the reference's)."""
+    g = load_golden('fwd_nh5_s%d' % seed)
+    _, g1, ve, g2, sp = build(seed)
+    for mod, key in ((g1, 'graph1'), (ve.value_network, 'value'), (g2, 'graph2'), (sp.human_motion_predictor, 'motion')):
+        sd = mod.state_dict()
+        assert list(sd.keys()) == list(g[key].keys()) or set(sd.keys()) == set(g[key].keys())
+        for k in sd:
+            assert torch.equal(sd[k], g[key][k]), (key, k)
+
+
+def test_state_dict_roundtrip_and_counts():
+    _, g1, ve, g2, sp = build(3)
+    assert sum(p.numel() for p in g1.parameters()) == 8256
+    assert sum(p.numel() for p in ve.parameters()) == 22813
+    assert sum(p.numel() for p in sp.parameters()) == 10693
+    _, h1, we, _, _ = build(4)
+    h1.load_state_dict(g1.state_dict())
+    we.value_network.load_state_dict(ve.value_network.state_dict())
+    for a, b in zip(h1.parameters(), g1.parameters()):
+        assert torch.equal(a, b)
+    assert [n for n, _ in ve.named_parameters()][:3] == ['graph_model.w_a', 'graph_model.w_r.0.weight', 'graph_model.w_r.0.bias']
+
+
+def test_deepcopy_gives_independent_target_model():
+    """trainer.py:40-41 deep-copies the value estimator as the target network."""
+    _, g1, ve, _, _ = build(0)
+    tgt = copy.deepcopy(ve)
+    assert tgt.graph_model is not ve.graph_model
+    assert tgt.graph_model._pack_cache is not ve.graph_model._pack_cache
+    with torch.no_grad():
+        ve.graph_model.w_a.add_(1.0)
+    assert not torch.equal(tgt.graph_model.w_a, ve.graph_model.w_a)
+
+
+def test_cpu_tensors_are_rejected_loudly():
+    _, g1, ve, _, sp = build(0)
+    robot, humans = torch.zeros(2, 1, 9), torch.zeros(2, 5, 5)
+    with pytest.raises(_lib.RglError):
+        g1((robot, humans))
+    with pytest.raises(_lib.RglError):
+        ve((robot, humans))
+    with pytest.raises(_lib.RglError):
+        sp((robot, humans), None)
+
+
+def test_batched_next_robot_state_rule():
+    robot = torch.tensor([[[1.5, -2.25, 0.1, 0.2, 0.3, 0.0, 4.0, 1.0, 1.57]], [[0.0, 1.0, 0.0, 0.0, 0.3, 0.0, 4.0, 1.0, 1.57]]])
+    out = compute_next_robot_state(robot, (0.3, -0.7), 0.25, 'holonomic')
+    for b in range(2):
+        exp = robot[b, 0].clone()
+        exp[0] = exp[0] + 0.3 * 0.25
+        exp[1] = exp[1] + (-0.7) * 0.25
+        exp[2] = 0.3
+        exp[3] = -0.7
+        assert torch.equal(out[b, 0], exp)
+    lin = LinearStatePredictor(policy_config(), 0.25)
+    hs = torch.rand(2, 3, 5)
+    nh = lin.linear_motion_approximator(hs)
+    assert torch.equal(nh[..., 0], hs[..., 0] + hs[..., 2]) and torch.equal(nh[..., 4], hs[..., 4])
