@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py -- RGL graph-forward states/sec (batch 4096, 5 humans) on N B200s, one rank per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload graph|value|statepred]
+
+A step = one pass of the hot path over one batch of `--batch` synthetic states (SURVEY.md 8(d) distribution).
+  value      device-resident throughput: inputs already in HBM, K steps replayed from CUDA graphs, timed with
+             CUDA events on the launching stream, max over ranks.
+  e2e        same metric through the host-buffer API (relationalgraphlearning_b200.hostio.HostStream):
+             every step copies its states from pinned host memory and reads the result back.
+  roofline   HBM fraction of the dominant kernel on algorithmic bytes (+ fp32-FMA fraction, the binding one).
+  cpu_baseline / --impl reference: the CPU oracle port of the reference path (oracle/rgl_oracle.py: same ATen
+             ops as crowd_nav/policy/graph_model.py) on the host cores.
+Inputs rotate through a pool larger than L2 (126 MB) so no step re-reads L2-resident states.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+L2_BYTES = 126 * 1024 * 1024
+FMA_PEAK_TFLOPS = 72.6         # measured on this pool's B200 with tools/fma_peak.cu (36.3 TFMA/s, 124.8 FMA/clk/SM)
+
+
+def algorithmic(workload, nh):
+    """(bytes, flops) per state: compulsory HBM I/O and 2*MAC."""
+    n = nh + 1
+    mac_graph = 2624 + 2368 * nh + (1024 * n + 32 * n * n) * 3
+    b_in = 36 + 20 * nh
+    if workload == 'graph':
+        return b_in + 128 * n, 2 * mac_graph
+    if workload == 'value':
+        return b_in + 4, 2 * (mac_graph + 14324)
+    return b_in + 20 * nh, 2 * (mac_graph + 2368 * n)
+
+
+def build_modules(seed=0):
+    from relationalgraphlearning_b200.config import policy_config
+    from relationalgraphlearning_b200.graph_model import RGL
+    from relationalgraphlearning_b200.state_predictor import StatePredictor
+    from relationalgraphlearning_b200.value_estimator import ValueEstimator
+    cfg = policy_config()
+    torch.manual_seed(seed)
+    g1 = RGL(cfg, 9, 5)
+    ve = ValueEstimator(cfg, g1)
+    g2 = RGL(cfg, 9, 5)
+    sp = StatePredictor(cfg, g2, 0.25)
+    return g1, ve, g2, sp
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.004):
+        super().__init__(daemon=True)
+        self.index, self.period, self.samples, self.reasons, self.stop_flag = index, period, [], set(), False
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {'hw_slowdown': nv.nvmlClocksThrottleReasonHwSlowdown,
+                 'hw_thermal_slowdown': nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 'sw_thermal_slowdown': nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 'sw_power_cap': nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(self.period)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {'sm_mhz': s[len(s) // 2] if s else None, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons),
+                'samples': len(s)}
+
+
+def cpu_reference_rate(workload, batch, nh, steps, warmup, budget_s=150.0):
+    """states/s of the oracle port (the reference's ATen op sequence) on the host cores."""
+    from oracle import rgl_oracle as O
+    from relationalgraphlearning_b200.synthetic import synthetic_states
+    g1, ve, g2, sp = build_modules(0)
+    sd = [{k: v.detach().clone() for k, v in m.state_dict().items()} for m in (g1, ve.value_network, g2, sp.human_motion_predictor)]
+    cores = torch.get_num_threads()
+    pool = [synthetic_states(batch, nh, seed=100 + i) for i in range(8)]
+
+    def step(i):
+        r, h = pool[i % len(pool)]
+        with torch.no_grad():
+            if workload == 'graph':
+                return O.rgl_forward(sd[0], r, h)
+            if workload == 'value':
+                return O.value_forward(sd[0], sd[1], r, h)
+            return O.statepred_forward(sd[2], sd[3], r, h)
+
+    for i in range(max(warmup, 3)):
+        step(i)
+    t0 = time.perf_counter()
+    step(0)
+    t1 = time.perf_counter() - t0
+    k = steps
+    sample = '%d steps x full batch %d' % (k, batch)
+    if t1 * k > budget_s:
+        k = max(10, int(budget_s / t1))
+        sample = '%d of %d steps x full batch %d (bounded to ~%.0f s of CPU work)' % (k, steps, batch, budget_s)
+    t0 = time.perf_counter()
+    for i in range(k):
+        step(i)
+    dt = time.perf_counter() - t0
+    return batch * k / dt, cores, sample, dt / k * 1e3, k
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=2000)
+    ap.add_argument('--warmup', type=int, default=20)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='graph', choices=['graph', 'value', 'statepred'])
+    ap.add_argument('--batch', type=int, default=4096)
+    ap.add_argument('--humans', type=int, default=5)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    B, nh, K, W = args.batch, args.humans, args.steps, max(args.warmup, 3)
+    abytes, aflops = algorithmic(args.workload, nh)
+    metric = 'RGL graph-forward states/sec (batch %d, %d humans)' % (B, nh)
+    config = {'workload': 'rgl_%s_forward B=%d Nh=%d 2-layer GCN fp32 (BASELINE configs[1])' % (args.workload, B, nh),
+              'batch_per_gpu': B, 'humans': nh, 'parallelism': 'dp%d (batch sharded, no collective)' % world,
+              'l2_policy': 'inputs rotate through a pool > 126 MB L2'}
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        rate, cores, sample, ms, k = cpu_reference_rate(args.workload, B, nh, K, W)
+        print(json.dumps({'impl': 'reference', 'metric': metric, 'value': rate, 'unit': 'states/s', 'n_gpus': args.gpus,
+                          'steps': k, 'warmup': W, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
+                          'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config,
+                          'cpu_baseline': {'value': rate, 'unit': 'states/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+                          'e2e': {'value': rate, 'unit': 'states/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+                          'gpu_launches': 0}))
+        return
+
+    import torch.distributed as dist
+    from relationalgraphlearning_b200 import ops
+    from relationalgraphlearning_b200.hostio import HostStream
+    from relationalgraphlearning_b200.synthetic import synthetic_states
+
+    assert torch.cuda.is_available(), 'bench.py (impl ours) needs a CUDA device'
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    g1, ve, g2, sp = build_modules(0)
+    ve.to(dev)
+    sp.to(dev)
+    module = {'graph': g1, 'value': ve, 'statepred': sp}[args.workload]
+
+    def run_step(robot, humans):
+        if args.workload == 'graph':
+            return g1.run(robot, humans, want_H=True)['H']
+        return module.run(robot, humans)
+
+    # ---- input pool larger than L2 (distinct states per rank) ----
+    pool_n = max(8, (int(1.15 * L2_BYTES) + B * (36 + 20 * nh) - 1) // (B * (36 + 20 * nh)))
+    rb, hb = synthetic_states(pool_n * B, nh, seed=1234 + rank)
+    robots = [rb[i * B:(i + 1) * B].contiguous() for i in range(pool_n)]
+    humans = [hb[i * B:(i + 1) * B].contiguous() for i in range(pool_n)]
+    robots_d = [r.to(dev) for r in robots]
+    humans_d = [h.to(dev) for h in humans]
+    config['input_pool_mb'] = round(pool_n * B * (36 + 20 * nh) / 1e6, 1)
+
+    # ---- warm-up (eager) + CUDA-graph capture of the steps ----
+    with torch.no_grad():
+        for i in range(W):
+            run_step(robots_d[i % pool_n], humans_d[i % pool_n])
+    torch.cuda.synchronize()
+    G = K
+    if K > 500:
+        G = max(d for d in range(1, 501) if K % d == 0)
+    reps = K // G
+    l0 = ops.LAUNCHES
+    side = torch.cuda.Stream()
+    graph = torch.cuda.CUDAGraph()
+    keep = []
+    with torch.no_grad(), torch.cuda.stream(side):
+        run_step(robots_d[0], humans_d[0])
+        torch.cuda.synchronize()
+        l0 = ops.LAUNCHES
+        with torch.cuda.graph(graph, stream=side):
+            for i in range(G):
+                keep.append(run_step(robots_d[(W + i) % pool_n], humans_d[(W + i) % pool_n]))
+                if len(keep) >= 64:     # rotate output buffers: a 64-deep ring (> L2 for the H output) instead of K live tensors
+                    keep = keep[32:]
+    launches_per_step = (ops.LAUNCHES - l0) / G
+    graph.replay()                      # untimed: uploads the graph, K more warm steps
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        graph.replay()
+    e1.record()
+    barrier()
+    t_ms = e0.elapsed_time(e1)
+
+    # ---- end to end through the host-buffer API: pinned host -> device -> kernels -> pinned host ----
+    robots_p = [r.pin_memory() for r in robots[:min(pool_n, 64)]]
+    humans_p = [h.pin_memory() for h in humans[:min(pool_n, 64)]]
+    hs = HostStream(args.workload, module, B, nh, dev, depth=4)
+    for i in range(W):
+        hs.submit(robots_p[i % len(robots_p)], humans_p[i % len(robots_p)])
+    hs.drain()
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record(hs.s_in)
+    checksum = 0.0
+    for i in range(K):
+        slot = hs.submit(robots_p[i % len(robots_p)], humans_p[i % len(robots_p)])
+        if i >= hs.depth - 1 and i % 256 == 0:
+            checksum += float(hs.result((slot + 1) % hs.depth).view(-1)[0])     # host actually consumes results
+    s1.record(hs.s_out)
+    hs.drain()
+    barrier()
+    e2e_ms = s0.elapsed_time(s1)
+    sampler.stop_flag = True
+    sampler.join()
+
+    times = torch.tensor([t_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    t_ms, e2e_ms = float(times[0]), float(times[1])
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:  # noqa: BLE001
+            pass
+        hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+        per_step_s = t_ms * 1e-3 / K
+        ach_gbs = abytes * B / per_step_s / 1e9
+        ach_tf = aflops * B / per_step_s / 1e12
+        out = {
+            'metric': metric, 'value': world * B * K / (t_ms * 1e-3), 'unit': 'states/s', 'n_gpus': world, 'steps': K,
+            'warmup': W, 'ms_per_step': t_ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic', 'config': config,
+            'e2e': {'value': world * B * K / (e2e_ms * 1e-3), 'unit': 'states/s', 'h2d_bytes_per_step': hs.h2d_bytes,
+                    'd2h_bytes_per_step': hs.d2h_bytes, 'ms_per_step': e2e_ms / K},
+            'gpu_launches': int(round(launches_per_step * K)),
+            'roofline': {'bound': 'hbm', 'achieved': ach_gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach_gbs / hbm_peak,
+                         'traffic': None, 'peak_source': 'measured' if peaks else 'fallback',
+                         'kernel': 'graph_forward_kernel', 'algorithmic_bytes_per_state': abytes,
+                         'fp32_fma': {'achieved_tflops': ach_tf, 'peak_tflops': FMA_PEAK_TFLOPS, 'frac': ach_tf / FMA_PEAK_TFLOPS,
+                                      'note': 'binding roofline: %d FLOP/B >> fp32 ridge' % (aflops // abytes)}},
+            'clocks': sampler.summary(),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            rate, cores, sample, ms, k = cpu_reference_rate(args.workload, B, nh, min(K, 2000), 3, budget_s=15.0)
+            out['cpu_baseline'] = {'value': rate, 'unit': 'states/s', 'cores': cores, 'kind': 'port', 'sample': sample,
+                                   'ms_per_step': ms}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -71,6 +71,7 @@ int rgl_pack_motion(const RglMotionParams* p, float* packed, rgl_stream_t stream
 int rgl_graph_forward(const float* robot, const float* humans, int B, int Nh, int humans_bcast,
                       const float* graph_packed, int num_layer, int flags, const float* motion_packed,
                       float* H, float* E, float* S, float* A0, rgl_stream_t stream) {
+    if (B == 0) return RGL_OK;          /* empty batch: nothing to do (empty tensors have null data pointers) */
     if (!robot || !humans || !graph_packed) return fail(RGL_EINVAL, "rgl_graph_forward: null input");
     if (!H && !E && !S) return fail(RGL_EINVAL, "rgl_graph_forward: no output requested");
     if (S && !motion_packed) return fail(RGL_EINVAL, "rgl_graph_forward: S requested without motion_packed");
@@ -95,6 +96,7 @@ int rgl_graph_forward(const float* robot, const float* humans, int B, int Nh, in
 }
 
 int rgl_value_head(const float* E, int B, const float* value_packed, float* V, rgl_stream_t stream) {
+    if (B == 0) return RGL_OK;
     if (!E || !value_packed || !V || B < 0) return fail(RGL_EINVAL, "rgl_value_head: bad argument");
     if (!aligned16(value_packed)) return fail(RGL_EALIGN, "rgl_value_head: packed weights must be 16-byte aligned");
     if (B == 0) return RGL_OK;
@@ -107,6 +109,7 @@ int rgl_value_head(const float* E, int B, const float* value_packed, float* V, r
 int rgl_value_forward(const float* robot, const float* humans, int B, int Nh, int humans_bcast,
                       const float* graph_packed, int num_layer, int flags, const float* value_packed,
                       float* E_scratch, float* V, float* A0, rgl_stream_t stream) {
+    if (B == 0) return RGL_OK;
     if (!E_scratch || !V) return fail(RGL_EINVAL, "rgl_value_forward: null output");
     int rc = rgl_graph_forward(robot, humans, B, Nh, humans_bcast, graph_packed, num_layer, flags, nullptr,
                                nullptr, E_scratch, nullptr, A0, stream);
@@ -116,6 +119,7 @@ int rgl_value_forward(const float* robot, const float* humans, int B, int Nh, in
 
 int rgl_gcn_layer(const float* X, const float* A, const float* W, const float* w_a, int B, int n, int flags,
                   float* Hout, float* Aout, rgl_stream_t stream) {
+    if (B == 0) return RGL_OK;
     if (!X || !W || !Hout || B < 0) return fail(RGL_EINVAL, "rgl_gcn_layer: bad argument");
     if (!A && !w_a) return fail(RGL_EINVAL, "rgl_gcn_layer: need A or w_a");
     if (n < 2 || n > RGL_MAX_HUMANS + 1) return fail(RGL_EUNSUPPORTED, "rgl_gcn_layer: n outside [2,32]");
@@ -132,6 +136,7 @@ int rgl_gcn_layer(const float* X, const float* A, const float* W, const float* w
 
 int rgl_plan_expand(const float* robot, const float* humans, int E, int Nh, const double* actions, int A, double time_step,
                     float* next_robot, float* reward, rgl_stream_t stream) {
+    if (E == 0) return RGL_OK;
     if (!robot || !actions || E < 0 || A < 1 || Nh < 0) return fail(RGL_EINVAL, "rgl_plan_expand: bad argument");
     if (reward && Nh > 0 && !humans) return fail(RGL_EINVAL, "rgl_plan_expand: reward needs humans");
     if (!next_robot && !reward) return fail(RGL_EINVAL, "rgl_plan_expand: no output requested");
@@ -143,6 +148,7 @@ int rgl_plan_expand(const float* robot, const float* humans, int E, int Nh, cons
 
 int rgl_plan_argmax(const float* reward, const float* V, int E, int A, float gamma_bar, float* value, int* best,
                     rgl_stream_t stream) {
+    if (E == 0) return RGL_OK;
     if (!reward || !V || E < 0 || A < 1 || (!value && !best)) return fail(RGL_EINVAL, "rgl_plan_argmax: bad argument");
     if (E == 0) return RGL_OK;
     cudaError_t e = rgl::run_plan_argmax(reward, V, E, A, gamma_bar, value, best, (cudaStream_t)stream);

@@ -46,6 +46,7 @@ def test_argument_validation_without_gpu():
     assert rc == -1 and b'null' in lib.rgl_last_error_string()
     rc = lib.rgl_value_head(None, 4, None, None, None)
     assert rc == -1
+    assert lib.rgl_value_head(None, 0, None, None, None) == 0      # empty batch is a no-op
 
 
 @pytest.mark.parametrize('seed', [0, 1, 2])
