@@ -134,9 +134,10 @@ int rgl_gcn_layer(const float* X, const float* A, const float* W, const float* w
  * For every (state e, action a): next robot state (state_predictor.py:41-60, holonomic) and the
  * reward estimate (model_predictive_rl.py:304-357 + crowd_sim/envs/utils/utils.py:4-26), in one
  * launch.  actions: DEVICE double [A,2] = (vx, vy) (model_predictive_rl.py:155-190 builds them in
- * float64).  Outputs: next_robot [E*A,1,9] fp32 (row e*A+a), reward [E*A] fp32.
+ * float64).  Outputs: next_robot [E*A,1,9] fp32 (row e*A+a), reward [E*A] fp32.  State e reads
+ * humans[e / humans_bcast] (look-ahead children of one parent share its predicted humans).
  * Reward arithmetic is float64 on the fp32 state values. */
-int rgl_plan_expand(const float* robot, const float* humans, int E, int Nh,
+int rgl_plan_expand(const float* robot, const float* humans, int E, int Nh, int humans_bcast,
                     const double* actions, int A, double time_step,
                     float* next_robot, float* reward, rgl_stream_t stream);
 

@@ -51,7 +51,7 @@ EXPORTS = {
                                          c_float_p, ctypes.c_void_p]),
     'rgl_gcn_layer': (ctypes.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, ctypes.c_int, ctypes.c_int,
                                      ctypes.c_int, c_float_p, c_float_p, ctypes.c_void_p]),
-    'rgl_plan_expand': (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+    'rgl_plan_expand': (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                        ctypes.c_int, ctypes.c_double, c_float_p, c_float_p, ctypes.c_void_p]),
     'rgl_plan_argmax': (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                        c_float_p, ctypes.c_void_p, ctypes.c_void_p]),

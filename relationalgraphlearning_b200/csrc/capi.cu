@@ -134,15 +134,16 @@ int rgl_gcn_layer(const float* X, const float* A, const float* W, const float* w
     return e == cudaSuccess ? RGL_OK : fail_cuda(e, "rgl_gcn_layer");
 }
 
-int rgl_plan_expand(const float* robot, const float* humans, int E, int Nh, const double* actions, int A, double time_step,
+int rgl_plan_expand(const float* robot, const float* humans, int E, int Nh, int humans_bcast, const double* actions, int A,
+                    double time_step,
                     float* next_robot, float* reward, rgl_stream_t stream) {
     if (E == 0) return RGL_OK;
-    if (!robot || !actions || E < 0 || A < 1 || Nh < 0) return fail(RGL_EINVAL, "rgl_plan_expand: bad argument");
+    if (!robot || !actions || E < 0 || A < 1 || Nh < 0 || humans_bcast < 1) return fail(RGL_EINVAL, "rgl_plan_expand: bad argument");
     if (reward && Nh > 0 && !humans) return fail(RGL_EINVAL, "rgl_plan_expand: reward needs humans");
     if (!next_robot && !reward) return fail(RGL_EINVAL, "rgl_plan_expand: no output requested");
     if ((long long)E * A > 0x7fffffffLL) return fail(RGL_EUNSUPPORTED, "rgl_plan_expand: E*A too large");
     if (E == 0) return RGL_OK;
-    cudaError_t e = rgl::run_plan_expand(robot, humans, E, Nh, actions, A, time_step, next_robot, reward, (cudaStream_t)stream);
+    cudaError_t e = rgl::run_plan_expand(robot, humans, E, Nh, humans_bcast, actions, A, time_step, next_robot, reward, (cudaStream_t)stream);
     return e == cudaSuccess ? RGL_OK : fail_cuda(e, "rgl_plan_expand");
 }
 

@@ -26,7 +26,7 @@ cudaError_t run_gcn_layer(const float* X, const float* A, const float* W, const 
 cudaError_t run_pack_graph(const RglGraphParams& p, float* out, cudaStream_t st);
 cudaError_t run_pack_value(const RglValueParams& p, float* out, cudaStream_t st);
 cudaError_t run_pack_motion(const RglMotionParams& p, float* out, cudaStream_t st);
-cudaError_t run_plan_expand(const float* robot, const float* humans, int E, int Nh, const double* actions, int A, double dt,
+cudaError_t run_plan_expand(const float* robot, const float* humans, int E, int Nh, int hb, const double* actions, int A, double dt,
                             float* next_robot, float* reward, cudaStream_t st);
 cudaError_t run_plan_argmax(const float* reward, const float* V, int E, int A, float gamma_bar, float* value, int* best,
                             cudaStream_t st);

@@ -52,7 +52,7 @@ __global__ void pack_motion_kernel(RglMotionParams p, float* out) {
 // ---- planner: one thread per (state e, action a) ------------------------------------------------------
 // next robot state: crowd_nav/policy/state_predictor.py:48-52 (fp32 position + fp32(v*dt), velocity = action)
 // reward:           crowd_nav/policy/model_predictive_rl.py:304-357, crowd_sim/envs/utils/utils.py:4-26, in float64
-__global__ void plan_expand_kernel(const float* __restrict__ robot, const float* __restrict__ humans, int E, int Nh,
+__global__ void plan_expand_kernel(const float* __restrict__ robot, const float* __restrict__ humans, int E, int Nh, int hb,
                                    const double* __restrict__ actions, int A, double dt,
                                    float* __restrict__ next_robot, float* __restrict__ reward) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -73,7 +73,7 @@ __global__ void plan_expand_kernel(const float* __restrict__ robot, const float*
         const double rpx = r[0], rpy = r[1], rrad = r[4], gx = r[5], gy = r[6];
         double dmin = INFINITY;
         bool collision = false;
-        const float* h = humans + (size_t)e * Nh * HD;
+        const float* h = humans + (size_t)(e / hb) * Nh * HD;
         for (int j = 0; j < Nh; ++j, h += HD) {
             const double px = (double)h[0] - rpx, py = (double)h[1] - rpy;
             const double vx = (double)h[2] - avx, vy = (double)h[3] - avy;
@@ -139,10 +139,10 @@ cudaError_t run_pack_motion(const RglMotionParams& p, float* out, cudaStream_t s
     pack_motion_kernel<<<4, 256, 0, st>>>(p, out);
     return cudaGetLastError();
 }
-cudaError_t run_plan_expand(const float* robot, const float* humans, int E, int Nh, const double* actions, int A, double dt,
+cudaError_t run_plan_expand(const float* robot, const float* humans, int E, int Nh, int hb, const double* actions, int A, double dt,
                             float* next_robot, float* reward, cudaStream_t st) {
     const int total = E * A;
-    plan_expand_kernel<<<(total + 127) / 128, 128, 0, st>>>(robot, humans, E, Nh, actions, A, dt, next_robot, reward);
+    plan_expand_kernel<<<(total + 127) / 128, 128, 0, st>>>(robot, humans, E, Nh, hb, actions, A, dt, next_robot, reward);
     return cudaGetLastError();
 }
 cudaError_t run_plan_argmax(const float* reward, const float* V, int E, int A, float gamma_bar, float* value, int* best,

@@ -170,15 +170,15 @@ def gcn_layer(X, W, A=None, w_a=None, skip=False, return_A=False):
     return (Hout, Aout) if return_A else Hout
 
 
-def plan_expand(robot, humans, actions, time_step, want_next=True, want_reward=True):
-    """robot[E,1,9], humans[E,Nh,5], actions double[A,2] -> next_robot[E*A,1,9], reward[E*A]."""
+def plan_expand(robot, humans, actions, time_step, humans_bcast=1, want_next=True, want_reward=True):
+    """robot[E,1,9], humans[E/humans_bcast,Nh,5], actions double[A,2] -> next_robot[E*A,1,9], reward[E*A]."""
     robot, humans = _check_state(robot, humans)
     E, Nh, A = robot.size(0), humans.size(1), actions.size(0)
     assert actions.dtype == torch.float64 and actions.is_cuda and actions.is_contiguous()
     nxt = torch.empty(E * A, 1, 9, dtype=torch.float32, device=robot.device) if want_next else None
     rew = torch.empty(E * A, dtype=torch.float32, device=robot.device) if want_reward else None
     with torch.cuda.device(robot.device):
-        rc = _lib.lib().rgl_plan_expand(_lib.ptr(robot), _lib.ptr(humans), E, Nh, _lib.ptr(actions), A, float(time_step),
+        rc = _lib.lib().rgl_plan_expand(_lib.ptr(robot), _lib.ptr(humans), E, Nh, humans_bcast, _lib.ptr(actions), A, float(time_step),
                                         _lib.ptr(nxt), _lib.ptr(rew), _lib.stream_ptr(robot.device))
     _lib.check(rc, 'rgl_plan_expand')
     _count(1 if E > 0 else 0)
