@@ -141,6 +141,7 @@ def main():
     ap.add_argument('--batch', type=int, default=4096)
     ap.add_argument('--humans', type=int, default=5)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--streams', type=int, default=3, help='CUDA streams the independent steps are issued on')
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', 0))
@@ -151,7 +152,8 @@ def main():
     metric = 'RGL graph-forward states/sec (batch %d, %d humans)' % (B, nh)
     config = {'workload': 'rgl_%s_forward B=%d Nh=%d 2-layer GCN fp32 (BASELINE configs[1])' % (args.workload, B, nh),
               'batch_per_gpu': B, 'humans': nh, 'parallelism': 'dp%d (batch sharded, no collective)' % world,
-              'l2_policy': 'inputs rotate through a pool > 126 MB L2'}
+              'l2_policy': 'inputs rotate through a pool > 126 MB L2',
+              'streams': args.streams}
 
     if args.impl == 'reference':
         if rank != 0:
@@ -205,7 +207,11 @@ def main():
         G = max(d for d in range(1, 501) if K % d == 0)
     reps = K // G
     l0 = ops.LAUNCHES
+    # Steps are independent batches, so consecutive steps are issued round-robin on `--streams` CUDA streams (forked
+    # from / joined to the capture stream): the tail of step i overlaps the head of step i+1 on the GPU.
+    nstreams = max(1, args.streams)
     side = torch.cuda.Stream()
+    branches = [torch.cuda.Stream() for _ in range(nstreams)]
     graph = torch.cuda.CUDAGraph()
     keep = []
     with torch.no_grad(), torch.cuda.stream(side):
@@ -213,10 +219,20 @@ def main():
         torch.cuda.synchronize()
         l0 = ops.LAUNCHES
         with torch.cuda.graph(graph, stream=side):
+            fork = torch.cuda.Event()
+            fork.record(side)
+            for b in branches:
+                b.wait_event(fork)
             for i in range(G):
-                keep.append(run_step(robots_d[(W + i) % pool_n], humans_d[(W + i) % pool_n]))
+                with torch.cuda.stream(branches[i % nstreams]):
+                    out = run_step(robots_d[(W + i) % pool_n], humans_d[(W + i) % pool_n])
+                    keep.append(out)
                 if len(keep) >= 64:     # rotate output buffers: a 64-deep ring (> L2 for the H output) instead of K live tensors
                     keep = keep[32:]
+            for b in branches:
+                ev = torch.cuda.Event()
+                ev.record(b)
+                side.wait_event(ev)
     launches_per_step = (ops.LAUNCHES - l0) / G
     graph.replay()                      # untimed: uploads the graph, K more warm steps
     torch.cuda.synchronize()
