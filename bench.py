@@ -185,8 +185,8 @@ def main():
 
     def run_step(robot, humans):
         if args.workload == 'graph':
-            return g1.run(robot, humans, want_H=True)['H']
-        return module.run(robot, humans)
+            return g1.run(robot, humans, want_H=True, throughput=args.streams > 1)['H']
+        return module.run(robot, humans, throughput=args.streams > 1)
 
     # ---- input pool larger than L2 (distinct states per rank) ----
     pool_n = max(8, (int(1.15 * L2_BYTES) + B * (36 + 20 * nh) - 1) // (B * (36 + 20 * nh)))

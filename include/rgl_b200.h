@@ -48,6 +48,8 @@ extern "C" {
 /* flags for the graph kernels */
 #define RGL_FLAG_SKIP       1         /* config.gcn.skip_connection  (graph_model.py:126-127) */
 #define RGL_FLAG_LAYERWISE  2         /* config.gcn.layerwise_graph  (graph_model.py:120-122) */
+#define RGL_FLAG_THROUGHPUT 4         /* scheduling hint: the caller keeps several independent launches in flight
+                                         (multi-stream serving); prefer the two-CTAs-per-SM kernel variant */
 
 typedef void* rgl_stream_t;
 

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_PKG, 'librgl_b200.so')
 MAX_LAYERS = 4
 FLAG_SKIP = 1
 FLAG_LAYERWISE = 2
+FLAG_THROUGHPUT = 4
 
 c_float_p = ctypes.c_void_p
 

@@ -600,7 +600,7 @@ static cudaError_t dispatch_tile(const GraphArgs& a, int num_sms, size_t max_sme
             // large batches: 32-row register tiles + 2 rows per thread in the per-state phases (least shared-memory
             // traffic per FFMA), two 6-warp CTAs per SM; up to one wave of tiles: 16-row tiles, 12 warps per CTA
             static const char* force = getenv("RGL_GRAPH_VARIANT");
-            const bool big = force ? (force[0] == '4') : (tiles32 > num_sms);
+            const bool big = force ? (force[0] == '4') : (tiles32 > num_sms || (a.flags & RGL_FLAG_THROUGHPUT));
             if (big) return launch_graph<32, 4, 6, 2>(a, num_sms, max_smem, st);
         }
         return launch_graph<32, 2, N, 0>(a, num_sms, max_smem, st);

@@ -38,8 +38,8 @@ class HostStream(object):
 
     def _run(self, robot, humans):
         if self.kind == 'graph':
-            return self.module.run(robot, humans, want_H=True)['H']
-        return self.module.run(robot, humans)
+            return self.module.run(robot, humans, want_H=True, throughput=True)['H']
+        return self.module.run(robot, humans, throughput=True)
 
     def _sequence(self, k, robot_h, humans_h):
         self.robot_d[k].copy_(robot_h, non_blocking=True)

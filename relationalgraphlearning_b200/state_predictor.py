@@ -65,10 +65,11 @@ class StatePredictor(nn.Module):
         g = self.graph_model
         return hasattr(g, 'kernel_supported') and g.kernel_supported() and self._dims == [64, 5]
 
-    def run(self, robot, humans, humans_bcast=1):
+    def run(self, robot, humans, humans_bcast=1, throughput=False):
         """One launch: graph kernel with the motion head, no autograd.  -> next_humans[B,Nh,5]."""
         mblob = ops.packed_motion(self.human_motion_predictor, self._pack_cache)
-        return self.graph_model.run(robot, humans, humans_bcast=humans_bcast, motion_blob=mblob, want_S=True)['S']
+        return self.graph_model.run(robot, humans, humans_bcast=humans_bcast, motion_blob=mblob, want_S=True,
+                                    throughput=throughput)['S']
 
     def _torch_humans(self, robot, humans, detach):
         emb = TM.graph_forward(self.graph_model, robot, humans)

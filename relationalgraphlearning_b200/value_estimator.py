@@ -32,9 +32,9 @@ class ValueEstimator(nn.Module):
         g = self.graph_model
         return hasattr(g, 'kernel_supported') and g.kernel_supported() and self._dims == [32, 100, 100, 1]
 
-    def run(self, robot, humans, humans_bcast=1):
+    def run(self, robot, humans, humans_bcast=1, throughput=False):
         """Two launches (graph kernel, value head), no autograd."""
-        E = self.graph_model.run(robot, humans, humans_bcast=humans_bcast, want_E=True)['E']
+        E = self.graph_model.run(robot, humans, humans_bcast=humans_bcast, want_E=True, throughput=throughput)['E']
         return ops.value_head_raw(ops.packed_value(self.value_network, self._pack_cache), E)
 
     def forward(self, state):
