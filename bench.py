@@ -102,8 +102,8 @@ def cpu_reference_rate(workload, batch, nh, steps, warmup, budget_s=150.0):
     from relationalgraphlearning_b200.synthetic import synthetic_states
     g1, ve, g2, sp = build_modules(0)
     sd = [{k: v.detach().clone() for k, v in m.state_dict().items()} for m in (g1, ve.value_network, g2, sp.human_motion_predictor)]
-    cores = torch.get_num_threads()
     pool = [synthetic_states(batch, nh, seed=100 + i) for i in range(8)]
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
 
     def step(i):
         r, h = pool[i % len(pool)]
@@ -114,6 +114,20 @@ def cpu_reference_rate(workload, batch, nh, steps, warmup, budget_s=150.0):
                 return O.value_forward(sd[0], sd[1], r, h)
             return O.statepred_forward(sd[2], sd[3], r, h)
 
+    # torchrun exports OMP_NUM_THREADS=1; the baseline gets every host core it can use.  Small batched ops do not
+    # always scale to all cores, so the thread count is calibrated and the FASTEST setting is the one reported.
+    best_t, cores = None, avail
+    for nt in sorted({avail, max(1, avail // 2), max(1, avail // 4), min(avail, 16), min(avail, 8)}, reverse=True):
+        torch.set_num_threads(nt)
+        for i in range(3):
+            step(i)
+        t0 = time.perf_counter()
+        for i in range(5):
+            step(i)
+        dt = (time.perf_counter() - t0) / 5
+        if best_t is None or dt < best_t:
+            best_t, cores = dt, nt
+    torch.set_num_threads(cores)
     for i in range(max(warmup, 3)):
         step(i)
     t0 = time.perf_counter()

@@ -149,6 +149,51 @@ int rgl_plan_expand(const float* robot, const float* humans, int E, int Nh, int 
 int rgl_plan_argmax(const float* reward, const float* V, int E, int A, float gamma_bar,
                     float* value, int* best, rgl_stream_t stream);
 
+
+/* ---- training step (value estimator): forward with activation saves + backward building blocks -----------------
+ * Replaces what autograd does under crowd_nav/utils/trainer.py:122-131 (loss.backward() through
+ * ValueEstimator -> RGL).  The forward is the same fused kernels, additionally writing the activations the
+ * backward needs; the backward is a short sequence of the three kernels below (see training.py). */
+typedef struct RglGraphSave {          /* all state-major; NULL members are not written */
+    float* a1r;                        /* [B,64]    relu(w_r.0 r)                              */
+    float* a1h;                        /* [B,Nh,64] relu(w_h.0 h)                              */
+    float* X;                          /* [B,n,32]  node embeddings                            */
+    float* Y;                          /* [B,n,32]  X w_a                                      */
+    float* A;                          /* [B,n,n]   attention                                  */
+    float* M[RGL_MAX_LAYERS];          /* [B,n,32]  A H_{l-1}                                  */
+    float* Rl[RGL_MAX_LAYERS];         /* [B,n,32]  relu(M_l W_l) (pre-skip)                   */
+    float* Hl[RGL_MAX_LAYERS];         /* [B,n,32]  H_l                                        */
+} RglGraphSave;
+
+/* row r of a logical [R,width] matrix = ptr + (r / rows_per_group) * group_stride + (r % rows_per_group) * ld
+ * (rows_per_group <= 1 and group_stride == 0: a plain matrix with leading dimension ld) */
+typedef struct RglRows {
+    float* ptr;
+    int ld;
+    int rows_per_group;
+    long long group_stride;
+} RglRows;
+
+/* rgl_graph_forward with saves; layerwise graphs are not supported here (RGL_EUNSUPPORTED). H / E optional. */
+int rgl_graph_forward_train(const float* robot, const float* humans, int B, int Nh,
+                            const float* graph_packed, int num_layer, int flags,
+                            const RglGraphSave* save, float* H, float* E, rgl_stream_t stream);
+/* rgl_value_head with saves: v0 [B,32], v1 [B,128], v2 [B,128] (hidden activations, 100 wide zero-padded). */
+int rgl_value_head_train(const float* E, int B, const float* value_packed, float* V,
+                         float* v0, float* v1, float* v2, rgl_stream_t stream);
+/* Backward of y = x W (+ b) over R rows: G [R,N] upstream gradient (multiplied by (mask > 0) when mask is given),
+ * Xin [R,K] the layer input.  Any of: Gin [R,K] (= or +=) needs W; dW and db are ATOMICALLY ACCUMULATED (zero them
+ * first).  w_layout 0: W/dW are [N][K] (nn.Linear.weight); 1: [K][N] (w_a, Ws).  N, K <= 128. */
+int rgl_linear_bwd(const RglRows* G, int N, const RglRows* mask, const RglRows* Xin, int K,
+                   const float* W, int w_layout, const RglRows* Gin, int accumulate,
+                   float* dW, float* db, int R, rgl_stream_t stream);
+/* gHprev[b,j,:] = (skip ? gH[b,j,:] : 0) + sum_i A[b,i,j] gM[b,i,:];  gA[b,i,j] (+)= gM[b,i,:] . Hprev[b,j,:] */
+int rgl_attn_layer_bwd(const float* A, const float* Hprev, const float* gM, const float* gH, int skip,
+                       float* gHprev, float* gA, int accumulate_gA, int B, int n, rgl_stream_t stream);
+/* softmax + similarity backward: gY = gS X, gX += gS^T Y with gS = A (gA - rowsum(gA A)) */
+int rgl_sim_bwd(const float* A, const float* gA, const float* X, const float* Y, float* gY, float* gX,
+                int B, int n, rgl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

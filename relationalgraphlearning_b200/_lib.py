@@ -34,6 +34,15 @@ class MotionParams(ctypes.Structure):
     _fields_ = [('w0', c_float_p), ('b0', c_float_p), ('w1', c_float_p), ('b1', c_float_p)]
 
 
+class GraphSave(ctypes.Structure):
+    _fields_ = [('a1r', c_float_p), ('a1h', c_float_p), ('X', c_float_p), ('Y', c_float_p), ('A', c_float_p),
+                ('M', c_float_p * MAX_LAYERS), ('Rl', c_float_p * MAX_LAYERS), ('Hl', c_float_p * MAX_LAYERS)]
+
+
+class Rows(ctypes.Structure):
+    _fields_ = [('ptr', c_float_p), ('ld', ctypes.c_int), ('rows_per_group', ctypes.c_int), ('group_stride', ctypes.c_longlong)]
+
+
 EXPORTS = {
     'rgl_version': (ctypes.c_int, []),
     'rgl_last_error_string': (ctypes.c_char_p, []),
@@ -52,6 +61,17 @@ EXPORTS = {
                                          c_float_p, ctypes.c_void_p]),
     'rgl_gcn_layer': (ctypes.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, ctypes.c_int, ctypes.c_int,
                                      ctypes.c_int, c_float_p, c_float_p, ctypes.c_void_p]),
+    'rgl_graph_forward_train': (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_int, ctypes.c_int, c_float_p, ctypes.c_int,
+                                               ctypes.c_int, ctypes.POINTER(GraphSave), c_float_p, c_float_p, ctypes.c_void_p]),
+    'rgl_value_head_train': (ctypes.c_int, [c_float_p, ctypes.c_int, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p,
+                                            ctypes.c_void_p]),
+    'rgl_linear_bwd': (ctypes.c_int, [ctypes.POINTER(Rows), ctypes.c_int, ctypes.POINTER(Rows), ctypes.POINTER(Rows), ctypes.c_int,
+                                      c_float_p, ctypes.c_int, ctypes.POINTER(Rows), ctypes.c_int, c_float_p, c_float_p,
+                                      ctypes.c_int, ctypes.c_void_p]),
+    'rgl_attn_layer_bwd': (ctypes.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, ctypes.c_int, c_float_p, c_float_p,
+                                          ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    'rgl_sim_bwd': (ctypes.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, ctypes.c_int, ctypes.c_int,
+                                   ctypes.c_void_p]),
     'rgl_plan_expand': (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                        ctypes.c_int, ctypes.c_double, c_float_p, c_float_p, ctypes.c_void_p]),
     'rgl_plan_argmax': (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_float,

@@ -88,7 +88,8 @@ int rgl_graph_forward(const float* robot, const float* humans, int B, int Nh, in
     rgl::GraphArgs a;
     a.robot = robot; a.humans = humans; a.B = B; a.Nh = Nh; a.hb = humans_bcast;
     a.gw = graph_packed; a.mw = S ? motion_packed : nullptr; a.L = num_layer; a.flags = flags;
-    a.H = H; a.E = E; a.S = S; a.A0 = A0; a.ntiles = 0;
+    a.H = H; a.E = E; a.S = S; a.A0 = A0; a.ntiles = 0; a.save = 0;
+    memset(&a.sv, 0, sizeof(a.sv));
     a.use_tma = (humans_bcast == 1 && aligned16(robot) && aligned16(humans)) ? 1 : 0;
     cudaError_t e = rgl::run_graph_forward(a, d.sms, d.max_smem, (cudaStream_t)stream);
     if (e == cudaErrorInvalidConfiguration) return fail(RGL_EUNSUPPORTED, "rgl_graph_forward: tile does not fit in shared memory");
@@ -102,7 +103,7 @@ int rgl_value_head(const float* E, int B, const float* value_packed, float* V, r
     if (B == 0) return RGL_OK;
     DevInfo d;
     if (int rc = dev_info(&d)) return rc;
-    cudaError_t e = rgl::run_value_head(E, B, value_packed, V, aligned16(E) ? 1 : 0, d.sms, (cudaStream_t)stream);
+    cudaError_t e = rgl::run_value_head(E, B, value_packed, V, nullptr, nullptr, nullptr, aligned16(E) ? 1 : 0, d.sms, (cudaStream_t)stream);
     return e == cudaSuccess ? RGL_OK : fail_cuda(e, "rgl_value_head");
 }
 
@@ -154,6 +155,77 @@ int rgl_plan_argmax(const float* reward, const float* V, int E, int A, float gam
     if (E == 0) return RGL_OK;
     cudaError_t e = rgl::run_plan_argmax(reward, V, E, A, gamma_bar, value, best, (cudaStream_t)stream);
     return e == cudaSuccess ? RGL_OK : fail_cuda(e, "rgl_plan_argmax");
+}
+
+int rgl_graph_forward_train(const float* robot, const float* humans, int B, int Nh, const float* graph_packed, int num_layer,
+                            int flags, const RglGraphSave* save, float* H, float* E, rgl_stream_t stream) {
+    if (B == 0) return RGL_OK;
+    if (!robot || !humans || !graph_packed || !save) return fail(RGL_EINVAL, "rgl_graph_forward_train: null argument");
+    if (flags & RGL_FLAG_LAYERWISE) return fail(RGL_EUNSUPPORTED, "rgl_graph_forward_train: layerwise graphs are not supported");
+    if (flags & ~(RGL_FLAG_SKIP | RGL_FLAG_THROUGHPUT)) return fail(RGL_EINVAL, "rgl_graph_forward_train: unknown flag");
+    if (B < 0 || Nh < 1 || Nh > RGL_MAX_HUMANS) return fail(RGL_EUNSUPPORTED, "rgl_graph_forward_train: bad batch / human count");
+    if (num_layer < 1 || num_layer > RGL_MAX_LAYERS) return fail(RGL_EUNSUPPORTED, "rgl_graph_forward_train: num_layer out of range");
+    if (!save->a1r || !save->a1h || !save->X || !save->Y || !save->A) return fail(RGL_EINVAL, "rgl_graph_forward_train: missing save buffer");
+    for (int l = 0; l < num_layer; ++l)
+        if (!save->M[l] || !save->Rl[l] || !save->Hl[l]) return fail(RGL_EINVAL, "rgl_graph_forward_train: missing per-layer save buffer");
+    if (!aligned16(graph_packed) || !aligned16(save->a1r) || !aligned16(save->a1h) || !aligned16(save->X) || !aligned16(save->Y))
+        return fail(RGL_EALIGN, "rgl_graph_forward_train: buffers must be 16-byte aligned");
+    DevInfo d;
+    if (int rc = dev_info(&d)) return rc;
+    rgl::GraphArgs a;
+    a.robot = robot; a.humans = humans; a.B = B; a.Nh = Nh; a.hb = 1;
+    a.gw = graph_packed; a.mw = nullptr; a.L = num_layer; a.flags = flags;
+    a.H = H; a.E = E; a.S = nullptr; a.A0 = nullptr; a.ntiles = 0; a.save = 1; a.sv = *save;
+    a.use_tma = (aligned16(robot) && aligned16(humans)) ? 1 : 0;
+    cudaError_t e = rgl::run_graph_forward(a, d.sms, d.max_smem, (cudaStream_t)stream);
+    if (e == cudaErrorInvalidConfiguration) return fail(RGL_EUNSUPPORTED, "rgl_graph_forward_train: tile does not fit in shared memory");
+    return e == cudaSuccess ? RGL_OK : fail_cuda(e, "rgl_graph_forward_train");
+}
+
+int rgl_value_head_train(const float* E, int B, const float* value_packed, float* V, float* v0, float* v1, float* v2,
+                         rgl_stream_t stream) {
+    if (B == 0) return RGL_OK;
+    if (!E || !value_packed || !V || !v0 || !v1 || !v2 || B < 0) return fail(RGL_EINVAL, "rgl_value_head_train: bad argument");
+    if (!aligned16(value_packed)) return fail(RGL_EALIGN, "rgl_value_head_train: packed weights must be 16-byte aligned");
+    DevInfo d;
+    if (int rc = dev_info(&d)) return rc;
+    cudaError_t e = rgl::run_value_head(E, B, value_packed, V, v0, v1, v2, aligned16(E) ? 1 : 0, d.sms, (cudaStream_t)stream);
+    return e == cudaSuccess ? RGL_OK : fail_cuda(e, "rgl_value_head_train");
+}
+
+int rgl_linear_bwd(const RglRows* G, int N, const RglRows* mask, const RglRows* Xin, int K, const float* W, int w_layout,
+                   const RglRows* Gin, int accumulate, float* dW, float* db, int R, rgl_stream_t stream) {
+    if (R == 0) return RGL_OK;
+    if (!G || !G->ptr || R < 0) return fail(RGL_EINVAL, "rgl_linear_bwd: null gradient");
+    if (N < 1 || N > 128 || K < 1 || K > 128) return fail(RGL_EUNSUPPORTED, "rgl_linear_bwd: N, K must be in [1,128]");
+    if (w_layout != 0 && w_layout != 1) return fail(RGL_EINVAL, "rgl_linear_bwd: bad w_layout");
+    if (Gin && Gin->ptr && !W) return fail(RGL_EINVAL, "rgl_linear_bwd: data gradient needs W");
+    if (dW && (!Xin || !Xin->ptr)) return fail(RGL_EINVAL, "rgl_linear_bwd: weight gradient needs Xin");
+    if ((!Gin || !Gin->ptr) && !dW && !db) return fail(RGL_EINVAL, "rgl_linear_bwd: no output requested");
+    DevInfo d;
+    if (int rc = dev_info(&d)) return rc;
+    cudaError_t e = rgl::run_linear_bwd(G, N, mask, Xin, K, W, w_layout, Gin, accumulate, dW, db, R, d.sms, d.max_smem, (cudaStream_t)stream);
+    return e == cudaSuccess ? RGL_OK : fail_cuda(e, "rgl_linear_bwd");
+}
+
+int rgl_attn_layer_bwd(const float* A, const float* Hprev, const float* gM, const float* gH, int skip, float* gHprev, float* gA,
+                       int accumulate_gA, int B, int n, rgl_stream_t stream) {
+    if (B == 0) return RGL_OK;
+    if (!A || !Hprev || !gM || !gHprev || !gA || (skip && !gH) || B < 0 || n < 1 || n > 32)
+        return fail(RGL_EINVAL, "rgl_attn_layer_bwd: bad argument");
+    if (!aligned16(Hprev) || !aligned16(gM) || !aligned16(gHprev) || (gH && !aligned16(gH)))
+        return fail(RGL_EALIGN, "rgl_attn_layer_bwd: row buffers must be 16-byte aligned");
+    cudaError_t e = rgl::run_attn_layer_bwd(A, Hprev, gM, gH, skip, gHprev, gA, accumulate_gA, B, n, (cudaStream_t)stream);
+    return e == cudaSuccess ? RGL_OK : fail_cuda(e, "rgl_attn_layer_bwd");
+}
+
+int rgl_sim_bwd(const float* A, const float* gA, const float* X, const float* Y, float* gY, float* gX, int B, int n,
+                rgl_stream_t stream) {
+    if (B == 0) return RGL_OK;
+    if (!A || !gA || !X || !Y || !gY || !gX || B < 0 || n < 1 || n > 32) return fail(RGL_EINVAL, "rgl_sim_bwd: bad argument");
+    if (!aligned16(X) || !aligned16(Y) || !aligned16(gY) || !aligned16(gX)) return fail(RGL_EALIGN, "rgl_sim_bwd: row buffers must be 16-byte aligned");
+    cudaError_t e = rgl::run_sim_bwd(A, gA, X, Y, gY, gX, B, n, (cudaStream_t)stream);
+    return e == cudaSuccess ? RGL_OK : fail_cuda(e, "rgl_sim_bwd");
 }
 
 }  // extern "C"

@@ -193,6 +193,21 @@ graph_forward_kernel(const GraphArgs a) {
                 bias_tile<RT>(acc1, B0 + half * 32, cg);
                 tile_gemm_smallk<RT, 2>(acc1, xrow, W0 + half * 32 + cg * 4, HID, K0);
                 store_tile_relu<RT>(scr, cg, acc1);
+                if (a.save) {
+#pragma unroll
+                    for (int q = 0; q < RT; ++q) {
+                        const int s = sb + rg + 8 * q;
+                        if (s < cnt) {
+                            float* dst = agent == 0 ? a.sv.a1r + (size_t)(s0 + s) * HID
+                                                    : a.sv.a1h + ((size_t)(s0 + s) * Nh + (agent - 1)) * HID;
+#pragma unroll
+                            for (int m = 0; m < 2; ++m)
+                                *reinterpret_cast<float4*>(dst + half * 32 + cg * 4 + 16 * m) =
+                                    make_float4(fmaxf(acc1[q][4 * m], 0.f), fmaxf(acc1[q][4 * m + 1], 0.f),
+                                                fmaxf(acc1[q][4 * m + 2], 0.f), fmaxf(acc1[q][4 * m + 3], 0.f));
+                        }
+                    }
+                }
                 __syncwarp();
                 tile_gemm_pf<RT, 2, 32>(acc2, scr, LDX, W1 + half * 32 * XD + cg * 4, XD);
                 __syncwarp();
@@ -210,10 +225,23 @@ graph_forward_kernel(const GraphArgs a) {
         // raw inputs are dead: prefetch the next tile's states under this tile's GCN layers
         if (tile + (int)gridDim.x < a.ntiles) load_tile(tile + gridDim.x);
 
+        // training forward: copy a [R][36] smem buffer (agent-major rows) to a state-major [B,n,32] HBM tensor
+        auto dump_rows = [&](const float* buf, float* dst) {
+            for (int idx = tid; idx < R * 8; idx += blockDim.x) {
+                const int r = idx >> 3, c4 = idx & 7;
+                const int i = r / TS, s = r - i * TS;
+                if (s < cnt) *reinterpret_cast<float4*>(dst + ((size_t)(s0 + s) * n + i) * XD + 4 * c4) = lds128(buf + r * LDX + 4 * c4);
+            }
+        };
+        if (a.save) {
+            dump_rows(XB, a.sv.X);
+            dump_rows(YB, a.sv.Y);
+        }
+
         // ================= GCN layers =================
         for (int l = 0; l < a.L; ++l) {
             const bool last = (l == a.L - 1);
-            const bool robot_only = last && a.H == nullptr && a.S == nullptr;
+            const bool robot_only = last && a.H == nullptr && a.S == nullptr && !a.save;
             const int rows = robot_only ? TS : R;        // node rows that must be produced by this layer
 
             if (l == 0 || layerwise) {
@@ -387,6 +415,14 @@ graph_forward_kernel(const GraphArgs a) {
                     }
                 }
                 __syncthreads();
+                if (a.save && l == 0) {
+                    for (int idx = tid; idx < R * n; idx += blockDim.x) {
+                        const int r = idx / n, j = idx - r * n;
+                        const int i = r / TS, s = r - i * TS;
+                        const float v = N > 0 ? AB[r * NPS + j] : AB[(i * n + j) * TS + s];
+                        if (s < cnt) a.sv.A[((size_t)(s0 + s) * n + i) * n + j] = v;
+                    }
+                }
             }
 
             // ---- AH = A . H  (per state) ----
@@ -480,6 +516,7 @@ graph_forward_kernel(const GraphArgs a) {
                 }
             }
             __syncthreads();
+            if (a.save) dump_rows(YB, a.sv.M[l]);
 
             // ---- H' = relu(AH . W_l) (+ H), in place over XB; last layer streams the outputs to HBM ----
             for (int rb = warp; rb * RB < rows; rb += nwarps) {
@@ -497,11 +534,15 @@ graph_forward_kernel(const GraphArgs a) {
                         float4 v = make_float4(fmaxf(acc[q][4 * m], 0.f), fmaxf(acc[q][4 * m + 1], 0.f),
                                                fmaxf(acc[q][4 * m + 2], 0.f), fmaxf(acc[q][4 * m + 3], 0.f));
                         float* p = xo + q * 8 * LDX + cg * 4 + 16 * m;
+                        if (a.save && s < cnt)
+                            *reinterpret_cast<float4*>(a.sv.Rl[l] + ((size_t)(s0 + s) * n + agent) * XD + cg * 4 + 16 * m) = v;
                         if (skip) {
                             const float4 h = lds128(p);
                             v.x += h.x; v.y += h.y; v.z += h.z; v.w += h.w;
                         }
                         sts128(p, v);
+                        if (a.save && s < cnt)
+                            *reinterpret_cast<float4*>(a.sv.Hl[l] + ((size_t)(s0 + s) * n + agent) * XD + cg * 4 + 16 * m) = v;
                         if (last && s < cnt) {
                             const size_t gs = (size_t)(s0 + s);
                             if (a.H) *reinterpret_cast<float4*>(a.H + (gs * n + agent) * XD + cg * 4 + 16 * m) = v;

@@ -4,6 +4,8 @@
 
 namespace rgl {
 
+typedef RglGraphSave GraphSave;      // optional activation saves of the training forward (include/rgl_b200.h)
+
 struct GraphArgs {
     const float* robot;
     const float* humans;
@@ -17,10 +19,20 @@ struct GraphArgs {
     float* A0;
     int ntiles;
     int use_tma;
+    int save;                 // 1 = sv holds pointers (training forward); disables the robot-row-only last layer
+    GraphSave sv;
 };
 
 cudaError_t run_graph_forward(const GraphArgs& a, int num_sms, size_t max_smem, cudaStream_t st);
-cudaError_t run_value_head(const float* E, int B, const float* vw, float* V, int use_tma, int num_sms, cudaStream_t st);
+cudaError_t run_value_head(const float* E, int B, const float* vw, float* V, float* v0, float* v1, float* v2, int use_tma, int num_sms,
+                           cudaStream_t st);
+cudaError_t run_linear_bwd(const RglRows* G, int N, const RglRows* mask, const RglRows* Xin, int K, const float* W, int w_layout,
+                           const RglRows* Gin, int accumulate, float* dW, float* db, int R, int num_sms, size_t max_smem,
+                           cudaStream_t st);
+cudaError_t run_attn_layer_bwd(const float* A, const float* Hprev, const float* gM, const float* gH, int skip, float* gHprev,
+                               float* gA, int accumulate_gA, int B, int n, cudaStream_t st);
+cudaError_t run_sim_bwd(const float* A, const float* gA, const float* X, const float* Y, float* gY, float* gX, int B, int n,
+                        cudaStream_t st);
 cudaError_t run_gcn_layer(const float* X, const float* A, const float* W, const float* wa, int B, int n, int flags,
                           float* Hout, float* Aout, int num_sms, size_t max_smem, cudaStream_t st);
 cudaError_t run_pack_graph(const RglGraphParams& p, float* out, cudaStream_t st);

@@ -9,7 +9,8 @@ constexpr int VT = 32;            // rows (states) per tile
 constexpr int LDV = VHP + 4;      // 132: padded stride of the 128-wide hidden rows
 
 __global__ void __launch_bounds__(256, 1) value_head_kernel(const float* __restrict__ E, int B, const float* __restrict__ vwg,
-                                                            float* __restrict__ V, int ntiles, int use_tma) {
+                                                            float* __restrict__ V, float* __restrict__ sv0, float* __restrict__ sv1,
+                                                            float* __restrict__ sv2, int ntiles, int use_tma) {
     constexpr int RT = 2, RB = 16;
     extern __shared__ __align__(128) float smem[];
     uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem);
@@ -82,6 +83,12 @@ __global__ void __launch_bounds__(256, 1) value_head_kernel(const float* __restr
                                        fmaxf(acc[q][4 * m + 2], 0.f), fmaxf(acc[q][4 * m + 3], 0.f)));
         }
         __syncthreads();
+        if (sv0) {                                   // training forward: save relu(layer 0)
+            for (int idx = tid; idx < VT * XD; idx += blockDim.x) {
+                const int s = idx / XD, c = idx - s * XD;
+                if (s < cnt) sv0[(size_t)(s0 + s) * XD + c] = X1[s * LDX + c];
+            }
+        }
         // X0 is dead: prefetch the next tile's rows
         if (tile + (int)gridDim.x < ntiles) load_tile(tile + gridDim.x);
 
@@ -105,6 +112,12 @@ __global__ void __launch_bounds__(256, 1) value_head_kernel(const float* __restr
                                        fmaxf(acc[q][4 * m + 2], 0.f), fmaxf(acc[q][4 * m + 3], 0.f)));
         }
         __syncthreads();
+        if (sv1) {
+            for (int idx = tid; idx < VT * VHP; idx += blockDim.x) {
+                const int s = idx / VHP, c = idx - s * VHP;
+                if (s < cnt) sv1[(size_t)(s0 + s) * VHP + c] = H1[s * LDV + c];
+            }
+        }
         // layer 2: 100 -> 100 (padded 128), relu
         for (int it = warp; it < (VT / RB) * 4; it += nwarps) {
             const int rb = it >> 2, cb = it & 3;
@@ -125,6 +138,12 @@ __global__ void __launch_bounds__(256, 1) value_head_kernel(const float* __restr
                                        fmaxf(acc[q][4 * m + 2], 0.f), fmaxf(acc[q][4 * m + 3], 0.f)));
         }
         __syncthreads();
+        if (sv2) {
+            for (int idx = tid; idx < VT * VHP; idx += blockDim.x) {
+                const int s = idx / VHP, c = idx - s * VHP;
+                if (s < cnt) sv2[(size_t)(s0 + s) * VHP + c] = H2[s * LDV + c];
+            }
+        }
         // layer 3: 100 -> 1.  8 lanes per row, 16 (padded) k each, butterfly reduce.
         {
             const int row = tid >> 3, part = tid & 7;          // 256 threads = 32 rows x 8
@@ -148,7 +167,8 @@ __global__ void __launch_bounds__(256, 1) value_head_kernel(const float* __restr
 
 size_t value_smem_bytes() { return (4 + VALUE_FLOATS + 2 * VT * LDX + 2 * VT * LDV) * sizeof(float); }
 
-cudaError_t run_value_head(const float* E, int B, const float* vw, float* V, int use_tma, int num_sms, cudaStream_t st) {
+cudaError_t run_value_head(const float* E, int B, const float* vw, float* V, float* v0, float* v1, float* v2, int use_tma, int num_sms,
+                           cudaStream_t st) {
     static bool attr_set = false;
     const size_t smem = value_smem_bytes();
     if (!attr_set) {
@@ -158,7 +178,7 @@ cudaError_t run_value_head(const float* E, int B, const float* vw, float* V, int
     }
     const int ntiles = (B + VT - 1) / VT;
     const int grid = ntiles < num_sms ? ntiles : num_sms;
-    value_head_kernel<<<grid, 256, smem, st>>>(E, B, vw, V, ntiles, use_tma);
+    value_head_kernel<<<grid, 256, smem, st>>>(E, B, vw, V, v0, v1, v2, ntiles, use_tma);
     return cudaGetLastError();
 }
 

@@ -28,6 +28,9 @@ class ValueEstimator(nn.Module):
         new._pack_cache = ops._PackCache()
         return new
 
+    def _train_params(self):
+        return self.graph_model.param_tensors() + list(self.value_network.parameters())
+
     def kernel_supported(self):
         g = self.graph_model
         return hasattr(g, 'kernel_supported') and g.kernel_supported() and self._dims == [32, 100, 100, 1]
@@ -46,6 +49,9 @@ class ValueEstimator(nn.Module):
         if not self.kernel_supported():
             return self.value_network(self.graph_model(state)[:, 0, :])
         if ops._needs_grad(self, robot, humans):
+            from . import training
+            if training.native_supported(self) and not (robot.requires_grad or humans.requires_grad):
+                return training.value_forward_train(self, robot, humans)      # fused forward + hand-written backward
             params = self.graph_model.param_tensors() + list(self.value_network.parameters())
             return ops.fused_with_autograd(lambda: self.run(robot, humans),
                                            lambda: self.value_network(TM.graph_forward(self.graph_model, robot, humans)[:, 0, :]),

@@ -1,0 +1,99 @@
+"""Native training step (-m gpu): fused forward with saves + hand-written backward vs oracle autograd gradients
+(the oracle is the reference math with the out-of-place skip add; crowd_nav/utils/trainer.py:122-131)."""
+import pytest
+import torch
+
+from conftest import assert_close_scaled, load_golden
+from oracle import rgl_oracle as O
+from relationalgraphlearning_b200 import ops, training
+from relationalgraphlearning_b200.config import policy_config
+from relationalgraphlearning_b200.graph_model import RGL
+from relationalgraphlearning_b200.synthetic import synthetic_states
+from relationalgraphlearning_b200.value_estimator import ValueEstimator
+
+pytestmark = pytest.mark.gpu
+
+
+def build(seed, dev, **kw):
+    cfg = policy_config(**kw)
+    torch.manual_seed(seed)
+    g = RGL(cfg, 9, 5)
+    ve = ValueEstimator(cfg, g)
+    sd_g = {k: v.clone() for k, v in g.state_dict().items()}
+    sd_v = {k: v.clone() for k, v in ve.value_network.state_dict().items()}
+    ve.to(dev)
+    return ve, sd_g, sd_v
+
+
+@pytest.mark.parametrize('nh,B,kw', [(5, 64, {}), (5, 100, {}), (10, 257, {}), (20, 33, {}), (3, 50, {}),
+                                     (5, 64, dict(num_layer=1)), (5, 64, dict(num_layer=3)), (5, 96, dict(skip_connection=False))])
+def test_native_backward_matches_oracle_autograd(nh, B, kw, cuda_device):
+    ve, sd_g, sd_v = build(7, cuda_device, **kw)
+    assert training.native_supported(ve)
+    robot, humans = synthetic_states(B, nh, seed=B)
+    target = torch.linspace(-0.25, 1.0, B).unsqueeze(1)
+    before = ops.LAUNCHES
+    out = ve((robot.to(cuda_device), humans.to(cuda_device)))
+    loss = torch.nn.functional.mse_loss(out, target.to(cuda_device))
+    loss.backward()
+    assert ops.LAUNCHES - before >= 10          # the hand-written kernels ran (no torch-op recompute)
+    gkw = dict(skip_connection=kw.get('skip_connection', True))
+    pg = {k: v.clone().requires_grad_(True) for k, v in sd_g.items()}
+    pv = {k: v.clone().requires_grad_(True) for k, v in sd_v.items()}
+    ref = O.value_forward(pg, pv, robot, humans, **gkw)
+    lo = torch.nn.functional.mse_loss(ref, target)
+    lo.backward()
+    assert_close_scaled(out, ref, 1e-5, 'V')
+    for name, p in ve.graph_model.named_parameters():
+        assert p.grad is not None, name
+        assert_close_scaled(p.grad, pg[name].grad, 2e-4, 'grad graph ' + name)
+    for name, p in ve.value_network.named_parameters():
+        assert_close_scaled(p.grad, pv[name].grad, 2e-4, 'grad value ' + name)
+
+
+def test_training_steps_track_the_oracle(cuda_device):
+    """20 Adam steps of the value regression (trainer.py:79-85) on the GPU vs the same steps with the oracle on CPU."""
+    ve, sd_g, sd_v = build(3, cuda_device)
+    pg = {k: v.clone().requires_grad_(True) for k, v in sd_g.items()}
+    pv = {k: v.clone().requires_grad_(True) for k, v in sd_v.items()}
+    opt_gpu = torch.optim.Adam(ve.parameters(), lr=1e-3)
+    order = [n for n, _ in ve.named_parameters()]
+    cpu_params = [pg[n[len('graph_model.'):]] if n.startswith('graph_model.') else pv[n[len('value_network.'):]] for n in order]
+    opt_cpu = torch.optim.Adam(cpu_params, lr=1e-3)
+    robot, humans = synthetic_states(128, 5, seed=11)
+    target = (robot[:, 0, 0:1] * 0.1 + 0.2)
+    rd, hd, td = robot.to(cuda_device), humans.to(cuda_device), target.to(cuda_device)
+    for step in range(20):
+        opt_gpu.zero_grad()
+        lg = torch.nn.functional.mse_loss(ve((rd, hd)), td)
+        lg.backward()
+        opt_gpu.step()
+        opt_cpu.zero_grad()
+        lc = torch.nn.functional.mse_loss(O.value_forward(pg, pv, robot, humans), target)
+        lc.backward()
+        opt_cpu.step()
+        assert abs(float(lg.detach()) - float(lc.detach())) <= 1e-3 * max(1e-3, abs(float(lc.detach()))), (step, float(lg), float(lc))
+    assert float(lg.detach()) < 0.9 * float(torch.nn.functional.mse_loss(O.value_forward(sd_g, sd_v, robot, humans), target))
+
+
+def test_trainer_style_value_update_with_target_network(cuda_device):
+    """optimize_batch semantics (trainer.py:122-131): target = r + gamma_bar * deepcopy(model)(next)."""
+    import copy
+    ve, _, _ = build(5, cuda_device)
+    tgt = copy.deepcopy(ve)
+    opt = torch.optim.Adam(ve.parameters(), lr=1e-3)
+    robot, humans = synthetic_states(100, 5, seed=1, device=cuda_device)
+    nrobot, nhumans = synthetic_states(100, 5, seed=2, device=cuda_device)
+    rewards = torch.rand(100, 1, device=cuda_device)
+    losses = []
+    for _ in range(5):
+        opt.zero_grad()
+        out = ve((robot, humans))
+        target = rewards + pow(0.9, 0.25) * tgt((nrobot, nhumans))
+        loss = torch.nn.functional.mse_loss(out, target)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss.detach()))
+    assert all(torch.isfinite(p).all() for p in ve.parameters())
+    assert losses[-1] < losses[0]
+    assert all(p.grad is None for p in tgt.parameters())      # the target network is evaluated without autograd work
