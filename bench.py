@@ -145,13 +145,106 @@ def cpu_reference_rate(workload, batch, nh, steps, warmup, budget_s=150.0):
     return batch * k / dt, cores, sample, dt / k * 1e3, k
 
 
+def train_bench(args, rank, world, local):
+    """BASELINE configs[3]: value-net training step (forward + target forward + MSE + backward + Adam), batch per GPU
+    `--batch`, one flat gradient all-reduce per step when world > 1.  Extra workload; not the headline metric."""
+    import copy
+    import torch.distributed as dist
+    from relationalgraphlearning_b200 import ops, parallel
+    from relationalgraphlearning_b200.synthetic import synthetic_states
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    B, nh, K, W = args.batch, args.humans, args.steps, max(args.warmup, 3)
+    g1, ve, _, _ = build_modules(0)
+    ve.to(dev)
+    target = copy.deepcopy(ve)
+    opt = torch.optim.Adam(ve.parameters(), lr=1e-3)
+    red = parallel.FlatGradAllReducer(ve.parameters())
+    pool = []
+    for i in range(8):
+        r, h = synthetic_states(B, nh, seed=10 + i + 100 * rank, device=dev)
+        r2, h2 = synthetic_states(B, nh, seed=50 + i + 100 * rank, device=dev)
+        pool.append((r, h, torch.rand(B, 1, device=dev) * 1.25 - 0.25, r2, h2))
+    gamma_bar = pow(0.9, 0.25)
+
+    def step(i):
+        r, h, rew, r2, h2 = pool[i % len(pool)]
+        if world > 1:
+            return parallel.dp_value_step(ve, target, opt, red, r, h, rew, r2, h2, gamma_bar, B * world)
+        opt.zero_grad()
+        out = ve((r, h))
+        with torch.no_grad():
+            tgt = rew + gamma_bar * target((r2, h2))
+        loss = torch.nn.functional.mse_loss(out, tgt)
+        loss.backward()
+        opt.step()
+        return loss.detach()
+
+    for i in range(W):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    l0 = ops.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        loss = step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ms = float(t[0])
+        out = {'metric': 'RGL value-net training samples/sec (batch %d per GPU, %d humans)' % (B, nh),
+               'value': world * B * K / (ms * 1e-3), 'unit': 'samples/s', 'n_gpus': world, 'steps': K, 'warmup': W,
+               'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+               'data': 'synthetic', 'gpu_launches': ops.LAUNCHES - l0, 'final_loss': float(loss),
+               'config': {'workload': 'value-net train step B=%d Nh=%d (BASELINE configs[3]): fused fwd+saves, native bwd, Adam' % (B, nh),
+                          'grad_allreduce_bytes': red.numel * 4 if world > 1 else 0,
+                          'parallelism': 'dp%d, one flat all-reduce per step' % world}}
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import rgl_oracle as O
+            sd = [{k: v.detach().cpu().clone().requires_grad_(True) for k, v in m.state_dict().items()} for m in (g1, ve.value_network)]
+            sdt = [{k: v.detach().cpu().clone() for k, v in m.state_dict().items()} for m in (g1, ve.value_network)]
+            copt = torch.optim.Adam(list(sd[0].values()) + list(sd[1].values()), lr=1e-3)
+            cpool = [tuple(t.cpu() for t in p) for p in pool[:2]]
+            torch.set_num_threads(len(os.sched_getaffinity(0)))
+
+            def cstep(i):
+                r, h, rew, r2, h2 = cpool[i % 2]
+                copt.zero_grad()
+                out_ = O.value_forward(sd[0], sd[1], r, h)
+                tgt_ = rew + gamma_bar * O.value_forward(sdt[0], sdt[1], r2, h2)
+                torch.nn.functional.mse_loss(out_, tgt_).backward()
+                copt.step()
+            for i in range(2):
+                cstep(i)
+            t0 = time.perf_counter()
+            n = 0
+            while time.perf_counter() - t0 < 10.0:
+                cstep(n)
+                n += 1
+            dt = time.perf_counter() - t0
+            out['cpu_baseline'] = {'value': B * n / dt, 'unit': 'samples/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+                                   'sample': '%d full train steps (~10 s)' % n, 'ms_per_step': dt / n * 1e3}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=2000)
     ap.add_argument('--warmup', type=int, default=20)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='graph', choices=['graph', 'value', 'statepred'])
+    ap.add_argument('--workload', default='graph', choices=['graph', 'value', 'statepred', 'train'])
     ap.add_argument('--batch', type=int, default=4096)
     ap.add_argument('--humans', type=int, default=5)
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -161,6 +254,11 @@ def main():
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))
+    if args.workload == 'train':
+        if args.impl == 'reference':
+            print(json.dumps({'impl': 'reference', 'unavailable': 'train workload: the CPU leg is reported inside the ours arm (cpu_baseline)'}))
+            return
+        return train_bench(args, rank, world, local)
     B, nh, K, W = args.batch, args.humans, args.steps, max(args.warmup, 3)
     abytes, aflops = algorithmic(args.workload, nh)
     metric = 'RGL graph-forward states/sec (batch %d, %d humans)' % (B, nh)

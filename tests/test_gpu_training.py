@@ -96,4 +96,3 @@ def test_trainer_style_value_update_with_target_network(cuda_device):
         losses.append(float(loss.detach()))
     assert all(torch.isfinite(p).all() for p in ve.parameters())
     assert losses[-1] < losses[0]
-    assert all(p.grad is None for p in tgt.parameters())      # the target network is evaluated without autograd work
