@@ -160,7 +160,7 @@ def train_bench(args, rank, world, local):
     g1, ve, _, _ = build_modules(0)
     ve.to(dev)
     target = copy.deepcopy(ve)
-    opt = torch.optim.Adam(ve.parameters(), lr=1e-3)
+    opt = torch.optim.Adam(ve.parameters(), lr=1e-3, fused=True)
     red = parallel.FlatGradAllReducer(ve.parameters())
     pool = []
     for i in range(8):
@@ -214,7 +214,7 @@ def train_bench(args, rank, world, local):
             sdt = [{k: v.detach().cpu().clone() for k, v in m.state_dict().items()} for m in (g1, ve.value_network)]
             copt = torch.optim.Adam(list(sd[0].values()) + list(sd[1].values()), lr=1e-3)
             cpool = [tuple(t.cpu() for t in p) for p in pool[:2]]
-            torch.set_num_threads(len(os.sched_getaffinity(0)))
+            torch.set_num_threads(min(16, len(os.sched_getaffinity(0))))     # small autograd ops do not scale past ~16 threads
 
             def cstep(i):
                 r, h, rew, r2, h2 = cpool[i % 2]

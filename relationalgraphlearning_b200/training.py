@@ -45,17 +45,23 @@ class _ValueTrain(torch.autograd.Function):
         robot, humans = ops._check_state(robot, humans)
         B, Nh = robot.size(0), humans.size(1)
         n, L, dev = Nh + 1, g.num_layer, robot.device
-        f = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)   # noqa: E731
-        sv = dict(a1r=f(B, 64), a1h=f(B, Nh, 64), X=f(B, n, 32), Y=f(B, n, 32), A=f(B, n, n),
-                  M=[f(B, n, 32) for _ in range(L)], Rl=[f(B, n, 32) for _ in range(L)], Hl=[f(B, n, 32) for _ in range(L)])
+        # one flat allocation for every saved activation (views below), instead of ~15 small tensors
+        sizes = [B * 64, B * Nh * 64, B * n * 32, B * n * 32, B * n * n] + [B * n * 32] * (3 * L) + [B * 32, B, B * 32, B * 128, B * 128]
+        flat = torch.empty(sum((x + 3) & ~3 for x in sizes), dtype=torch.float32, device=dev)
+        views, off = [], 0
+        for x in sizes:
+            views.append(flat[off:off + x])
+            off += (x + 3) & ~3
+        sv = dict(a1r=views[0].view(B, 64), a1h=views[1].view(B, Nh, 64), X=views[2].view(B, n, 32), Y=views[3].view(B, n, 32),
+                  A=views[4].view(B, n, n), M=[views[5 + l].view(B, n, 32) for l in range(L)],
+                  Rl=[views[5 + L + l].view(B, n, 32) for l in range(L)], Hl=[views[5 + 2 * L + l].view(B, n, 32) for l in range(L)])
+        E, V, v0, v1, v2 = (views[5 + 3 * L].view(B, 32), views[6 + 3 * L].view(B, 1), views[7 + 3 * L].view(B, 32),
+                            views[8 + 3 * L].view(B, 128), views[9 + 3 * L].view(B, 128))
         cs = _lib.GraphSave()
         for k in ('a1r', 'a1h', 'X', 'Y', 'A'):
             setattr(cs, k, sv[k].data_ptr())
         for l in range(L):
             cs.M[l], cs.Rl[l], cs.Hl[l] = sv['M'][l].data_ptr(), sv['Rl'][l].data_ptr(), sv['Hl'][l].data_ptr()
-        E = f(B, 32)
-        V = f(B, 1)
-        v0, v1, v2 = f(B, 32), f(B, 128), f(B, 128)
         lib = _lib.lib()
         with torch.cuda.device(dev):
             rc = lib.rgl_graph_forward_train(_lib.ptr(robot), _lib.ptr(humans), B, Nh, _lib.ptr(ops.packed_graph(g)), L,
@@ -67,7 +73,7 @@ class _ValueTrain(torch.autograd.Function):
         ops._count(2)
         ctx.ve, ctx.sv, ctx.acts = ve, sv, (robot, humans, E, v0, v1, v2)
         ctx.nparams = len(params)
-        return V
+        return V.clone()
 
     @staticmethod
     def backward(ctx, gV):
@@ -78,15 +84,27 @@ class _ValueTrain(torch.autograd.Function):
         n, L, dev = Nh + 1, g.num_layer, robot.device
         skip = bool(g.skip_connection)
         gV = gV.contiguous().float()
-        z = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=dev)   # noqa: E731
-        f = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)   # noqa: E731
         vn = ve.value_network
-        gp = {id(p): z(*p.shape) for p in list(g.parameters()) + list(vn.parameters())}
+        plist = list(g.parameters()) + list(vn.parameters())
+        # one zero-filled flat buffer: [all parameter gradients | gH_L], one uninitialised flat buffer for the temporaries
+        psz = [(p.numel() + 3) & ~3 for p in plist]
+        zflat = torch.zeros(sum(psz) + B * n * 32, dtype=torch.float32, device=dev)
+        gp, off = {}, 0
+        for p, sz in zip(plist, psz):
+            gp[id(p)] = zflat[off:off + p.numel()].view(p.shape)
+            off += sz
+        gH0 = zflat[off:].view(B, n, 32)
+        tsz = [B * 128, B * 128, B * 32, B * n * n, B * n * 32, B * n * 32, B * 64, B * Nh * 64] + [B * n * 32] * L
+        tflat = torch.empty(sum((x + 3) & ~3 for x in tsz), dtype=torch.float32, device=dev)
+        tv, off = [], 0
+        for x in tsz:
+            tv.append(tflat[off:off + x])
+            off += (x + 3) & ~3
         G = lambda p: gp[id(p)]   # noqa: E731
         with torch.cuda.device(dev), torch.no_grad():
             # ---------------- value head: V = L6(relu(L4(relu(L2(relu(L0(E))))))) ----------------
-            g2, g1, g0 = f(B, 128), f(B, 128), f(B, 32)
-            gH = z(B, n, 32)                              # gradient w.r.t. H_L: only the robot row is non-zero
+            g2, g1, g0 = tv[0].view(B, 128), tv[1].view(B, 128), tv[2].view(B, 32)
+            gH = gH0                                      # gradient w.r.t. H_L: only the robot row is non-zero
             _linear_bwd(_rows(gV, 1), 1, _rows(v2, 128), 100, B, W=vn[6].weight, Gin=_rows(g2, 128), dW=G(vn[6].weight), db=G(vn[6].bias), dev=dev)
             _linear_bwd(_rows(g2, 128), 100, _rows(v1, 128), 100, B, W=vn[4].weight, mask=_rows(v2, 128), Gin=_rows(g1, 128),
                         dW=G(vn[4].weight), db=G(vn[4].bias), dev=dev)
@@ -95,14 +113,14 @@ class _ValueTrain(torch.autograd.Function):
             _linear_bwd(_rows(g0, 32), 32, _rows(E, 32), 32, B, W=vn[0].weight, mask=_rows(v0, 32),
                         Gin=_rows(gH, 32, 1, n * 32), dW=G(vn[0].weight), db=G(vn[0].bias), dev=dev)
             # ---------------- GCN layers, last to first ----------------
-            gA = f(B, n, n)
-            gM = f(B, n, 32)
+            gA = tv[3].view(B, n, n)
+            gM = tv[4].view(B, n, 32)
             lib = _lib.lib()
             for l in range(L - 1, -1, -1):
                 Hprev = sv['X'] if l == 0 else sv['Hl'][l - 1]
                 _linear_bwd(_rows(gH, 32), 32, _rows(sv['M'][l], 32), 32, B * n, W=g.Ws[l], w_layout=1, mask=_rows(sv['Rl'][l], 32),
                             Gin=_rows(gM, 32), dW=G(g.Ws[l]), dev=dev)
-                gHp = f(B, n, 32)
+                gHp = tv[8 + l].view(B, n, 32)
                 rc = lib.rgl_attn_layer_bwd(_lib.ptr(sv['A']), _lib.ptr(Hprev), _lib.ptr(gM), _lib.ptr(gH), 1 if skip else 0,
                                             _lib.ptr(gHp), _lib.ptr(gA), 0 if l == L - 1 else 1, B, n, _lib.stream_ptr(dev))
                 _lib.check(rc, 'rgl_attn_layer_bwd')
@@ -110,7 +128,7 @@ class _ValueTrain(torch.autograd.Function):
                 gH = gHp
             gX = gH                                         # gradient w.r.t. X from the layer stack
             # ---------------- similarity ----------------
-            gY = f(B, n, 32)
+            gY = tv[5].view(B, n, 32)
             rc = lib.rgl_sim_bwd(_lib.ptr(sv['A']), _lib.ptr(gA), _lib.ptr(sv['X']), _lib.ptr(sv['Y']), _lib.ptr(gY), _lib.ptr(gX),
                                  B, n, _lib.stream_ptr(dev))
             _lib.check(rc, 'rgl_sim_bwd')
@@ -118,7 +136,7 @@ class _ValueTrain(torch.autograd.Function):
             _linear_bwd(_rows(gY, 32), 32, _rows(sv['X'], 32), 32, B * n, W=g.w_a, w_layout=1, Gin=_rows(gX, 32), accumulate=True,
                         dW=G(g.w_a), dev=dev)
             # ---------------- embeddings: robot rows (node 0) and human rows (nodes 1..Nh) of gX ----------------
-            ga_r, ga_h = f(B, 64), f(B * Nh, 64)
+            ga_r, ga_h = tv[6].view(B, 64), tv[7].view(B * Nh, 64)
             _linear_bwd(_rows(gX, 32, 1, n * 32), 32, _rows(sv['a1r'], 64), 64, B, W=g.w_r[2].weight, mask=_rows(sv['X'], 32, 1, n * 32),
                         Gin=_rows(ga_r, 64), dW=G(g.w_r[2].weight), db=G(g.w_r[2].bias), dev=dev)
             _linear_bwd(_rows(ga_r, 64), 64, _rows(robot, 9), 9, B, mask=_rows(sv['a1r'], 64), dW=G(g.w_r[0].weight), db=G(g.w_r[0].bias), dev=dev)
