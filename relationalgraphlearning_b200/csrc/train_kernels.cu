@@ -30,11 +30,12 @@ struct LinBwdArgs {
     float* dW;            // optional, same layout as W
     float* db;            // optional [N]
     int ntiles;
+    int vecG, vecX;       // rows of G(+mask) / Xin are 16-byte aligned and N / K are multiples of 4
 };
 
 constexpr int LT = 64;    // rows per tile
 
-__global__ void __launch_bounds__(256, 1) rows_linear_bwd_kernel(const LinBwdArgs a) {
+__global__ void __launch_bounds__(256) rows_linear_bwd_kernel(const LinBwdArgs a) {
     extern __shared__ __align__(128) float smem[];
     const int N = a.N, K = a.K;
     const int NP4 = (N + 3) & ~3, NP32 = (N + 31) & ~31, KP32 = (K + 31) & ~31;
@@ -54,6 +55,8 @@ __global__ void __launch_bounds__(256, 1) rows_linear_bwd_kernel(const LinBwdArg
         }
     }
     const int KB = KP32 / 32, NB = NP32 / 32;            // weight-gradient blocks (<= 16 items, 2 per warp)
+    const int items = KB * NB;
+    const int nsplit = items >= 8 ? 1 : 8 / items;
     float wacc[2][32];
 #pragma unroll
     for (int t = 0; t < 2; ++t)
@@ -64,20 +67,46 @@ __global__ void __launch_bounds__(256, 1) rows_linear_bwd_kernel(const LinBwdArg
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
         const int r0 = tile * LT;
         __syncthreads();
-        // ---- stage G (masked) and Xin, zero padded ----
-        for (int idx = tid; idx < LT * ldg; idx += blockDim.x) {
-            const int r = idx / ldg, c = idx - r * ldg;
-            float v = 0.f;
-            if (r0 + r < a.R && c < N) {
-                v = a.G.row(r0 + r)[c];
-                if (a.mask.ptr && !(a.mask.row(r0 + r)[c] > 0.f)) v = 0.f;
+        // ---- stage G (masked) and Xin, zero padded (float4 path when every row is 16-byte aligned) ----
+        if (a.vecG) {
+            const int n4 = ldg >> 2;
+            for (int idx = tid; idx < LT * n4; idx += blockDim.x) {
+                const int r = idx / n4, c = (idx - r * n4) << 2;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r0 + r < a.R && c < N) {
+                    v = *reinterpret_cast<const float4*>(a.G.row(r0 + r) + c);
+                    if (a.mask.ptr) {
+                        const float4 m = *reinterpret_cast<const float4*>(a.mask.row(r0 + r) + c);
+                        v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f; v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
+                    }
+                }
+                sts128(Gs + r * ldg + c, v);
             }
-            Gs[idx] = v;
+        } else {
+            for (int idx = tid; idx < LT * ldg; idx += blockDim.x) {
+                const int r = idx / ldg, c = idx - r * ldg;
+                float v = 0.f;
+                if (r0 + r < a.R && c < N) {
+                    v = a.G.row(r0 + r)[c];
+                    if (a.mask.ptr && !(a.mask.row(r0 + r)[c] > 0.f)) v = 0.f;
+                }
+                Gs[idx] = v;
+            }
         }
         if (a.Xin.ptr) {
-            for (int idx = tid; idx < LT * ldx; idx += blockDim.x) {
-                const int r = idx / ldx, c = idx - r * ldx;
-                Xs[idx] = (r0 + r < a.R && c < K) ? a.Xin.row(r0 + r)[c] : 0.f;
+            if (a.vecX) {
+                const int k4 = ldx >> 2;
+                for (int idx = tid; idx < LT * k4; idx += blockDim.x) {
+                    const int r = idx / k4, c = (idx - r * k4) << 2;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (r0 + r < a.R && c < K) v = *reinterpret_cast<const float4*>(a.Xin.row(r0 + r) + c);
+                    sts128(Xs + r * ldx + c, v);
+                }
+            } else {
+                for (int idx = tid; idx < LT * ldx; idx += blockDim.x) {
+                    const int r = idx / ldx, c = idx - r * ldx;
+                    Xs[idx] = (r0 + r < a.R && c < K) ? a.Xin.row(r0 + r)[c] : 0.f;
+                }
             }
         }
         __syncthreads();
@@ -111,13 +140,17 @@ __global__ void __launch_bounds__(256, 1) rows_linear_bwd_kernel(const LinBwdArg
         if (a.dW) {
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
-                const int it = warp + 8 * t;
-                if (it < KB * NB) {
+                // >= 8 (k-block, n-block) items: item = warp + 8t over all rows; fewer: the rows of an item are split over
+                // nsplit warps (partials are combined through shared memory at the end)
+                int it, rbeg, rend;
+                if (nsplit == 1) { it = warp + 8 * t; rbeg = 0; rend = LT; }
+                else { it = warp % items; const int part = warp / items; rbeg = part * (LT / nsplit); rend = (t == 0 && part < nsplit) ? rbeg + LT / nsplit : rbeg; }
+                if (it < items && rbeg < rend) {
                     const int kb = it / NB, nb = it - kb * NB;
                     const float* xp = Xs + kb * 32 + rg * 4;
                     const float* gp = Gs + nb * 32 + cg * 8;
 #pragma unroll 4
-                    for (int r = 0; r < LT; ++r) {
+                    for (int r = rbeg; r < rend; ++r) {
                         const float4 xv = lds128(xp + r * ldx);
                         const float4 g0 = lds128(gp + r * ldg), g1 = lds128(gp + r * ldg + 4);
                         const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
@@ -140,18 +173,38 @@ __global__ void __launch_bounds__(256, 1) rows_linear_bwd_kernel(const LinBwdArg
     }
     // ---- flush the per-CTA partial sums ----
     if (a.dW) {
+        if (nsplit == 1) {
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-            const int it = warp + 8 * t;
-            if (it < KB * NB) {
+            for (int t = 0; t < 2; ++t) {
+                const int it = warp + 8 * t;
+                if (it < items) {
+                    const int kb = it / NB, nb = it - kb * NB;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int k = kb * 32 + rg * 4 + i, nn = nb * 32 + cg * 8 + j;
+                            if (k < K && nn < N) atomicAdd(a.dW + (a.w_layout == 0 ? (size_t)nn * K + k : (size_t)k * N + nn), wacc[t][8 * i + j]);
+                        }
+                }
+            }
+        } else {
+            // combine the row-split partials of each item in shared memory (Gs/Xs are free now), then one atomic per element
+            __syncthreads();
+            float* red = smem;                                 // [8 warps][1024]: the launcher allocates >= 32 KB
+            if (warp < items * nsplit) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) red[warp * 1024 + c * 32 + lane] = wacc[0][c];
+            }
+            __syncthreads();
+            for (int e = tid; e < items * 1024; e += blockDim.x) {
+                const int it = e >> 10, w = e & 1023;
+                const int c = w >> 5, ln = w & 31;             // accumulator c of lane ln
+                float sum = 0.f;
+                for (int part = 0; part < nsplit; ++part) sum += red[(part * items + it) * 1024 + w];
                 const int kb = it / NB, nb = it - kb * NB;
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int k = kb * 32 + rg * 4 + i, nn = nb * 32 + cg * 8 + j;
-                        if (k < K && nn < N) atomicAdd(a.dW + (a.w_layout == 0 ? (size_t)nn * K + k : (size_t)k * N + nn), wacc[t][8 * i + j]);
-                    }
+                const int k = kb * 32 + (ln & 7) * 4 + (c >> 3), nn = nb * 32 + (ln >> 3) * 8 + (c & 7);
+                if (k < K && nn < N) atomicAdd(a.dW + (a.w_layout == 0 ? (size_t)nn * K + k : (size_t)k * N + nn), sum);
             }
         }
     }
@@ -268,7 +321,8 @@ cudaError_t run_linear_bwd(const RglRows* G, int N, const RglRows* mask, const R
     a.N = N; a.K = K; a.R = R; a.W = W; a.w_layout = w_layout; a.accumulate = accumulate; a.dW = dW; a.db = db;
     a.ntiles = (R + LT - 1) / LT;
     const int NP4 = (N + 3) & ~3, NP32 = (N + 31) & ~31, KP32 = (K + 31) & ~31;
-    const size_t smem = ((size_t)NP4 * (KP32 + 4) + (size_t)LT * (NP32 + 4) + (size_t)LT * (KP32 + 4)) * sizeof(float);
+    size_t smem = ((size_t)NP4 * (KP32 + 4) + (size_t)LT * (NP32 + 4) + (size_t)LT * (KP32 + 4)) * sizeof(float);
+    if (dW && smem < 8 * 1024 * sizeof(float)) smem = 8 * 1024 * sizeof(float);      // row-split reduction scratch
     if (smem > max_smem) return cudaErrorInvalidConfiguration;
     static bool attr_set = false;
     if (!attr_set) {
@@ -276,7 +330,16 @@ cudaError_t run_linear_bwd(const RglRows* G, int N, const RglRows* mask, const R
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    const int grid = a.ntiles < num_sms ? a.ntiles : num_sms;
+    auto vec_ok = [](const Rows& r, int width) {
+        return r.ptr != nullptr && (reinterpret_cast<uintptr_t>(r.ptr) & 15u) == 0 && (r.ld & 3) == 0 && (r.gstride & 3) == 0 && (width & 3) == 0;
+    };
+    a.vecG = vec_ok(a.G, N) && (a.mask.ptr == nullptr || vec_ok(a.mask, N));
+    a.vecX = vec_ok(a.Xin, K);
+    // several CTAs per SM hide the global-load latency of the staging phase (the tiles are small)
+    int per_sm = (int)((200 * 1024) / (smem + 1024));
+    per_sm = per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm);
+    const int cap = num_sms * per_sm;
+    const int grid = a.ntiles < cap ? a.ntiles : cap;
     rows_linear_bwd_kernel<<<grid, 256, smem, st>>>(a);
     return cudaGetLastError();
 }
