@@ -35,7 +35,7 @@ struct LinBwdArgs {
 
 constexpr int LT = 64;    // rows per tile
 
-__global__ void __launch_bounds__(256) rows_linear_bwd_kernel(const LinBwdArgs a) {
+__global__ void __launch_bounds__(256, 2) rows_linear_bwd_kernel(const LinBwdArgs a) {
     extern __shared__ __align__(128) float smem[];
     const int N = a.N, K = a.K;
     const int NP4 = (N + 3) & ~3, NP32 = (N + 31) & ~31, KP32 = (K + 31) & ~31;
@@ -337,7 +337,7 @@ cudaError_t run_linear_bwd(const RglRows* G, int N, const RglRows* mask, const R
     a.vecX = vec_ok(a.Xin, K);
     // several CTAs per SM hide the global-load latency of the staging phase (the tiles are small)
     int per_sm = (int)((200 * 1024) / (smem + 1024));
-    per_sm = per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm);
+    per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);      // register budget: __launch_bounds__(256, 2)
     const int cap = num_sms * per_sm;
     const int grid = a.ntiles < cap ? a.ntiles : cap;
     rows_linear_bwd_kernel<<<grid, 256, smem, st>>>(a);
