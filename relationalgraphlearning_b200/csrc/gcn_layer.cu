@@ -10,11 +10,13 @@
 namespace rgl {
 
 template <int TS>
-__global__ void __launch_bounds__(384, 1) gcn_layer_kernel(const float* __restrict__ X, const float* __restrict__ Ag,
+__global__ void __launch_bounds__(TS == 32 ? 192 : 384, TS == 32 ? 2 : 1) gcn_layer_kernel(const float* __restrict__ X, const float* __restrict__ Ag,
                                                            const float* __restrict__ Wg, const float* __restrict__ wag,
                                                            int B, int n, int flags, float* __restrict__ Hout,
                                                            float* __restrict__ Aout, int ntiles) {
-    constexpr int RT = 2, RB = 16;
+    // TS = 32: 32-row register tiles (RT = 4, least shared-memory traffic per FFMA), one warp per 32 rows, two CTAs
+    // per SM so that the load / compute / store phases of different tiles overlap; TS = 16: 16-row tiles.
+    constexpr int RT = TS == 32 ? 4 : 2, RB = 8 * RT;
     extern __shared__ __align__(128) float smem[];
     const int R = n * TS;
     uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem);
@@ -73,7 +75,7 @@ __global__ void __launch_bounds__(384, 1) gcn_layer_kernel(const float* __restri
                 for (int q = 0; q < RT; ++q)
 #pragma unroll
                     for (int c = 0; c < 8; ++c) acc[q][c] = 0.f;
-                tile_gemm<RT, 2>(acc, XB + (rb * RB + rg) * LDX, LDX, WA + cg * 4, XD, XD);
+                tile_gemm_pf<RT, 2, XD>(acc, XB + (rb * RB + rg) * LDX, LDX, WA + cg * 4, XD);
 #pragma unroll
                 for (int q = 0; q < RT; ++q)
 #pragma unroll
@@ -148,7 +150,7 @@ __global__ void __launch_bounds__(384, 1) gcn_layer_kernel(const float* __restri
             for (int q = 0; q < RT; ++q)
 #pragma unroll
                 for (int c = 0; c < 8; ++c) acc[q][c] = 0.f;
-            tile_gemm<RT, 2>(acc, YB + (rb * RB + rg) * LDX, LDX, W + cg * 4, XD, XD);
+            tile_gemm_pf<RT, 2, XD>(acc, YB + (rb * RB + rg) * LDX, LDX, W + cg * 4, XD);
 #pragma unroll
             for (int q = 0; q < RT; ++q) {
                 const int r = rb * RB + rg + 8 * q;
@@ -185,11 +187,13 @@ static cudaError_t launch_gcn(const float* X, const float* A, const float* W, co
         attr_set = true;
     }
     const int ntiles = (B + TS - 1) / TS;
-    int nwarps = n * TS / 16;
-    if (nwarps > 12) nwarps = 12;
+    int nwarps = TS == 32 ? n : n * TS / 16;            // one warp per 32-row (TS = 32) / 16-row block
+    const int cap = TS == 32 ? 6 : 12;
+    if (nwarps > cap) nwarps = cap;
     int per_sm = (int)((228 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 2048 / (nwarps * 32)) per_sm = 2048 / (nwarps * 32);
+    const int max_cta = TS == 32 ? 2 : 1;               // register budget of the kernel's __launch_bounds__
+    if (per_sm > max_cta) per_sm = max_cta;
     const int grid = ntiles < num_sms * per_sm ? ntiles : num_sms * per_sm;
     gcn_layer_kernel<TS><<<grid, nwarps * 32, smem, st>>>(X, A, W, wa, B, n, flags, Hout, Aout, ntiles);
     return cudaGetLastError();
