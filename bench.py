@@ -428,7 +428,10 @@ def main():
                     'api': 'hostio.HostStream.submit (pinned host -> H2D -> kernels -> D2H -> pinned host, %d streams, CUDA-graph replay)' % depth},
             'gpu_launches': int(round(launches_per_step * K)),
             'roofline': {'bound': 'hbm', 'achieved': ach_gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach_gbs / hbm_peak,
-                         'traffic': None, 'peak_source': 'measured' if peaks else 'fallback',
+                         'traffic': 675072 if (args.workload == 'graph' and B == 4096 and nh == 5) else None,
+                         'traffic_note': 'dram__bytes_read+write of one launch from profiles/r1_final_graph_forward_b4096_full.md '
+                                         '(the 3.1 MB H output of a single profiled launch stays in the 126 MB L2: dram write = 0)',
+                         'peak_source': 'measured' if peaks else 'fallback',
                          'kernel': 'graph_forward_kernel', 'algorithmic_bytes_per_state': abytes,
                          'fp32_fma': {'achieved_tflops': ach_tf, 'peak_tflops': FMA_PEAK_TFLOPS, 'frac': ach_tf / FMA_PEAK_TFLOPS,
                                       'note': 'binding roofline: %d FLOP/B >> fp32 ridge' % (aflops // abytes)}},
