@@ -163,6 +163,7 @@ typedef struct RglGraphSave {          /* all state-major; NULL members are not 
     float* M[RGL_MAX_LAYERS];          /* [B,n,32]  A H_{l-1}                                  */
     float* Rl[RGL_MAX_LAYERS];         /* [B,n,32]  relu(M_l W_l) (pre-skip)                   */
     float* Hl[RGL_MAX_LAYERS];         /* [B,n,32]  H_l                                        */
+    float* mh;                         /* [B,Nh,64] relu(motion.0 H_L) (only with S; may be NULL) */
 } RglGraphSave;
 
 /* row r of a logical [R,width] matrix = ptr + (r / rows_per_group) * group_stride + (r % rows_per_group) * ld
@@ -177,7 +178,8 @@ typedef struct RglRows {
 /* rgl_graph_forward with saves; layerwise graphs are not supported here (RGL_EUNSUPPORTED). H / E optional. */
 int rgl_graph_forward_train(const float* robot, const float* humans, int B, int Nh,
                             const float* graph_packed, int num_layer, int flags,
-                            const RglGraphSave* save, float* H, float* E, rgl_stream_t stream);
+                            const float* motion_packed, const RglGraphSave* save,
+                            float* H, float* E, float* S, rgl_stream_t stream);
 /* rgl_value_head with saves: v0 [B,32], v1 [B,128], v2 [B,128] (hidden activations, 100 wide zero-padded). */
 int rgl_value_head_train(const float* E, int B, const float* value_packed, float* V,
                          float* v0, float* v1, float* v2, rgl_stream_t stream);

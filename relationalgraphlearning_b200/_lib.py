@@ -36,7 +36,7 @@ class MotionParams(ctypes.Structure):
 
 class GraphSave(ctypes.Structure):
     _fields_ = [('a1r', c_float_p), ('a1h', c_float_p), ('X', c_float_p), ('Y', c_float_p), ('A', c_float_p),
-                ('M', c_float_p * MAX_LAYERS), ('Rl', c_float_p * MAX_LAYERS), ('Hl', c_float_p * MAX_LAYERS)]
+                ('M', c_float_p * MAX_LAYERS), ('Rl', c_float_p * MAX_LAYERS), ('Hl', c_float_p * MAX_LAYERS), ('mh', c_float_p)]
 
 
 class Rows(ctypes.Structure):
@@ -62,7 +62,8 @@ EXPORTS = {
     'rgl_gcn_layer': (ctypes.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, ctypes.c_int, ctypes.c_int,
                                      ctypes.c_int, c_float_p, c_float_p, ctypes.c_void_p]),
     'rgl_graph_forward_train': (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_int, ctypes.c_int, c_float_p, ctypes.c_int,
-                                               ctypes.c_int, ctypes.POINTER(GraphSave), c_float_p, c_float_p, ctypes.c_void_p]),
+                                               ctypes.c_int, c_float_p, ctypes.POINTER(GraphSave), c_float_p, c_float_p, c_float_p,
+                                               ctypes.c_void_p]),
     'rgl_value_head_train': (ctypes.c_int, [c_float_p, ctypes.c_int, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p,
                                             ctypes.c_void_p]),
     'rgl_linear_bwd': (ctypes.c_int, [ctypes.POINTER(Rows), ctypes.c_int, ctypes.POINTER(Rows), ctypes.POINTER(Rows), ctypes.c_int,

@@ -158,7 +158,8 @@ int rgl_plan_argmax(const float* reward, const float* V, int E, int A, float gam
 }
 
 int rgl_graph_forward_train(const float* robot, const float* humans, int B, int Nh, const float* graph_packed, int num_layer,
-                            int flags, const RglGraphSave* save, float* H, float* E, rgl_stream_t stream) {
+                            int flags, const float* motion_packed, const RglGraphSave* save, float* H, float* E, float* S,
+                            rgl_stream_t stream) {
     if (B == 0) return RGL_OK;
     if (!robot || !humans || !graph_packed || !save) return fail(RGL_EINVAL, "rgl_graph_forward_train: null argument");
     if (flags & RGL_FLAG_LAYERWISE) return fail(RGL_EUNSUPPORTED, "rgl_graph_forward_train: layerwise graphs are not supported");
@@ -174,8 +175,10 @@ int rgl_graph_forward_train(const float* robot, const float* humans, int B, int 
     if (int rc = dev_info(&d)) return rc;
     rgl::GraphArgs a;
     a.robot = robot; a.humans = humans; a.B = B; a.Nh = Nh; a.hb = 1;
-    a.gw = graph_packed; a.mw = nullptr; a.L = num_layer; a.flags = flags;
-    a.H = H; a.E = E; a.S = nullptr; a.A0 = nullptr; a.ntiles = 0; a.save = 1; a.sv = *save;
+    if (S && (!motion_packed || !aligned16(motion_packed))) return fail(RGL_EINVAL, "rgl_graph_forward_train: S needs 16-byte aligned motion_packed");
+    if (!H && !E && !S) return fail(RGL_EINVAL, "rgl_graph_forward_train: no output requested");
+    a.gw = graph_packed; a.mw = S ? motion_packed : nullptr; a.L = num_layer; a.flags = flags;
+    a.H = H; a.E = E; a.S = S; a.A0 = nullptr; a.ntiles = 0; a.save = 1; a.sv = *save;
     a.use_tma = (aligned16(robot) && aligned16(humans)) ? 1 : 0;
     cudaError_t e = rgl::run_graph_forward(a, d.sms, d.max_smem, (cudaStream_t)stream);
     if (e == cudaErrorInvalidConfiguration) return fail(RGL_EUNSUPPORTED, "rgl_graph_forward_train: tile does not fit in shared memory");

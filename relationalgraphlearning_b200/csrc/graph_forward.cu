@@ -566,6 +566,20 @@ graph_forward_kernel(const GraphArgs a) {
                         bias_tile<RT>(acc1, mw + M_B0 + half * 32, cg);
                         tile_gemm_pf<RT, 2, XD>(acc1, xo, LDX, mw + M_W0 + half * 32 + cg * 4, MH);
                         store_tile_relu<RT>(scr, cg, acc1);
+                        if (a.save && a.sv.mh) {
+#pragma unroll
+                            for (int q = 0; q < RT; ++q) {
+                                const int s = r0 + rg + 8 * q - agent * TS;
+                                if (s < cnt) {
+                                    float* dst = a.sv.mh + ((size_t)(s0 + s) * Nh + (agent - 1)) * MH + half * 32 + cg * 4;
+#pragma unroll
+                                    for (int m = 0; m < 2; ++m)
+                                        *reinterpret_cast<float4*>(dst + 16 * m) =
+                                            make_float4(fmaxf(acc1[q][4 * m], 0.f), fmaxf(acc1[q][4 * m + 1], 0.f),
+                                                        fmaxf(acc1[q][4 * m + 2], 0.f), fmaxf(acc1[q][4 * m + 3], 0.f));
+                                }
+                            }
+                        }
                         __syncwarp();
                         const float* hrow = YB + (r0 + rl) * LDX + kh * KPL;
 #pragma unroll

@@ -61,6 +61,10 @@ class StatePredictor(nn.Module):
         new._pack_cache = ops._PackCache()
         return new
 
+    def _train_params(self, detach=False):
+        mp = list(self.human_motion_predictor.parameters())
+        return mp if detach else self.graph_model.param_tensors() + mp
+
     def kernel_supported(self):
         g = self.graph_model
         return hasattr(g, 'kernel_supported') and g.kernel_supported() and self._dims == [64, 5]
@@ -87,6 +91,10 @@ class StatePredictor(nn.Module):
         if not self.kernel_supported():
             next_humans = self._torch_humans(robot, humans, detach)
         elif ops._needs_grad(self, robot, humans):
+            from . import training
+            if training.native_supported(self) and not (robot.requires_grad or humans.requires_grad):
+                # fused forward with saves + hand-written backward (detach => only the motion head gets gradients)
+                return [next_robot, training.statepred_forward_train(self, robot, humans, bool(detach))]
             params = list(self.human_motion_predictor.parameters())
             if not detach:
                 params = self.graph_model.param_tensors() + params

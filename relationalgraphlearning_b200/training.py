@@ -1,14 +1,16 @@
-"""Native training step of the value estimator: fused forward with activation saves + hand-written backward.
+"""Native training steps: fused forward with activation saves + hand-written backward.
 
-`value_forward_train(ve, robot, humans)` is what `ValueEstimator.forward` dispatches to when gradients are
-required (crowd_nav/utils/trainer.py:80,123 followed by loss.backward()).  Forward = the same fused sm_100a
-kernels as inference, additionally writing the activations the backward needs; backward = the kernel sequence
-below (csrc/train_kernels.cu), producing the gradient of every parameter of `graph_model` and `value_network`.
+`value_forward_train(ve, robot, humans)` / `statepred_forward_train(sp, robot, humans, detach)` are what
+`ValueEstimator.forward` / `StatePredictor.forward` dispatch to when gradients are required
+(crowd_nav/utils/trainer.py:80,95,123,144 followed by loss.backward()).  Forward = the same fused sm_100a kernels
+as inference, additionally writing the activations the backward needs; backward = the kernel sequence below
+(csrc/train_kernels.cu), producing the gradient of every parameter.
 
-  value head   4 x rgl_linear_bwd                     (gV -> gE, dW/db of the 4 Linear layers)
-  per layer    rgl_linear_bwd (W_l, relu mask)  ->  rgl_attn_layer_bwd (A^T gM, gA += gM H^T)
-  similarity   rgl_sim_bwd (softmax + Y X^T)    ->  rgl_linear_bwd (w_a)
-  embedding    2 x rgl_linear_bwd per agent kind (robot rows / human rows of the [B,n,32] gradient, grouped-row view)
+  value head    4 x rgl_linear_bwd                    (gV -> gE, dW/db of the 4 Linear layers)
+  motion head   2 x rgl_linear_bwd                    (gS -> gH_L on the human rows)
+  per layer     rgl_linear_bwd (W_l, relu mask)  ->  rgl_attn_layer_bwd (A^T gM, gA += gM H^T)
+  similarity    rgl_sim_bwd (softmax + Y X^T)    ->  rgl_linear_bwd (w_a)
+  embedding     2 x rgl_linear_bwd per agent kind (robot rows / human rows of the [B,n,32] gradient, grouped-row view)
 """
 import ctypes
 
@@ -27,15 +29,94 @@ def _rows(t, ld=None, rows_per_group=0, group_stride=0, offset=0):
 
 
 def _linear_bwd(G, N, Xin, K, R, W=None, w_layout=0, mask=None, Gin=None, accumulate=False, dW=None, db=None, dev=None):
-    lib = _lib.lib()
-    rc = lib.rgl_linear_bwd(ctypes.byref(G), N, ctypes.byref(mask) if mask is not None else None,
-                            ctypes.byref(Xin) if Xin is not None else None, K,
-                            _lib.ptr(W) if W is not None else None, w_layout,
-                            ctypes.byref(Gin) if Gin is not None else None, 1 if accumulate else 0,
-                            _lib.ptr(dW) if dW is not None else None, _lib.ptr(db) if db is not None else None,
-                            R, _lib.stream_ptr(dev))
+    rc = _lib.lib().rgl_linear_bwd(ctypes.byref(G), N, ctypes.byref(mask) if mask is not None else None,
+                                   ctypes.byref(Xin) if Xin is not None else None, K,
+                                   _lib.ptr(W) if W is not None else None, w_layout,
+                                   ctypes.byref(Gin) if Gin is not None else None, 1 if accumulate else 0,
+                                   _lib.ptr(dW) if dW is not None else None, _lib.ptr(db) if db is not None else None,
+                                   R, _lib.stream_ptr(dev))
     _lib.check(rc, 'rgl_linear_bwd')
     ops._count(1)
+
+
+def _carve(sizes, dev, zero=False):
+    """One flat fp32 allocation carved into 16-byte aligned 1-D views (1 alloc / 1 fill instead of one per tensor)."""
+    flat = (torch.zeros if zero else torch.empty)(sum((x + 3) & ~3 for x in sizes), dtype=torch.float32, device=dev)
+    views, off = [], 0
+    for x in sizes:
+        views.append(flat[off:off + x])
+        off += (x + 3) & ~3
+    return views
+
+
+def _graph_forward_train(g, robot, humans, extra_sizes, motion_blob=None, want_E=False, want_S=False):
+    """Fused graph forward with saves.  Returns (saves dict, extra views, E or None, S or None)."""
+    B, Nh = robot.size(0), humans.size(1)
+    n, L, dev = Nh + 1, g.num_layer, robot.device
+    sizes = [B * 64, B * Nh * 64, B * n * 32, B * n * 32, B * n * n] + [B * n * 32] * (3 * L) + \
+            [B * 32 if want_E else 0, B * Nh * 5 if want_S else 0, B * Nh * 64 if want_S else 0] + list(extra_sizes)
+    v = _carve(sizes, dev)
+    sv = dict(a1r=v[0].view(B, 64), a1h=v[1].view(B, Nh, 64), X=v[2].view(B, n, 32), Y=v[3].view(B, n, 32), A=v[4].view(B, n, n),
+              M=[v[5 + l].view(B, n, 32) for l in range(L)], Rl=[v[5 + L + l].view(B, n, 32) for l in range(L)],
+              Hl=[v[5 + 2 * L + l].view(B, n, 32) for l in range(L)])
+    E = v[5 + 3 * L].view(B, 32) if want_E else None
+    S = v[6 + 3 * L].view(B, Nh, 5) if want_S else None
+    sv['mh'] = v[7 + 3 * L].view(B, Nh, 64) if want_S else None
+    cs = _lib.GraphSave()
+    for k in ('a1r', 'a1h', 'X', 'Y', 'A'):
+        setattr(cs, k, sv[k].data_ptr())
+    for l in range(L):
+        cs.M[l], cs.Rl[l], cs.Hl[l] = sv['M'][l].data_ptr(), sv['Rl'][l].data_ptr(), sv['Hl'][l].data_ptr()
+    cs.mh = sv['mh'].data_ptr() if want_S else None
+    with torch.cuda.device(dev):
+        rc = _lib.lib().rgl_graph_forward_train(_lib.ptr(robot), _lib.ptr(humans), B, Nh, _lib.ptr(ops.packed_graph(g)), L, g.flags(),
+                                                _lib.ptr(motion_blob) if want_S else None, ctypes.byref(cs), None,
+                                                _lib.ptr(E), _lib.ptr(S), _lib.stream_ptr(dev))
+    _lib.check(rc, 'rgl_graph_forward_train')
+    ops._count(1)
+    return sv, v[8 + 3 * L:], E, S
+
+
+def _graph_backward(g, sv, robot, humans, gH, G, dev):
+    """Back-propagate gH = dLoss/dH_L [B,n,32] through the GCN layers, the similarity and the embeddings.
+    G(p) returns the (zero-initialised) gradient buffer of parameter p; gradients are accumulated into them."""
+    B, Nh = robot.size(0), humans.size(1)
+    n, L = Nh + 1, g.num_layer
+    skip = bool(g.skip_connection)
+    lib = _lib.lib()
+    t = _carve([B * n * n, B * n * 32, B * n * 32, B * 64, B * Nh * 64] + [B * n * 32] * L, dev)
+    gA, gM, gY, ga_r, ga_h = t[0].view(B, n, n), t[1].view(B, n, 32), t[2].view(B, n, 32), t[3].view(B, 64), t[4].view(B * Nh, 64)
+    for l in range(L - 1, -1, -1):
+        Hprev = sv['X'] if l == 0 else sv['Hl'][l - 1]
+        _linear_bwd(_rows(gH, 32), 32, _rows(sv['M'][l], 32), 32, B * n, W=g.Ws[l], w_layout=1, mask=_rows(sv['Rl'][l], 32),
+                    Gin=_rows(gM, 32), dW=G(g.Ws[l]), dev=dev)
+        gHp = t[5 + l].view(B, n, 32)
+        rc = lib.rgl_attn_layer_bwd(_lib.ptr(sv['A']), _lib.ptr(Hprev), _lib.ptr(gM), _lib.ptr(gH), 1 if skip else 0,
+                                    _lib.ptr(gHp), _lib.ptr(gA), 0 if l == L - 1 else 1, B, n, _lib.stream_ptr(dev))
+        _lib.check(rc, 'rgl_attn_layer_bwd')
+        ops._count(1)
+        gH = gHp
+    gX = gH                                         # gradient w.r.t. X from the layer stack
+    rc = lib.rgl_sim_bwd(_lib.ptr(sv['A']), _lib.ptr(gA), _lib.ptr(sv['X']), _lib.ptr(sv['Y']), _lib.ptr(gY), _lib.ptr(gX),
+                         B, n, _lib.stream_ptr(dev))
+    _lib.check(rc, 'rgl_sim_bwd')
+    ops._count(1)
+    _linear_bwd(_rows(gY, 32), 32, _rows(sv['X'], 32), 32, B * n, W=g.w_a, w_layout=1, Gin=_rows(gX, 32), accumulate=True,
+                dW=G(g.w_a), dev=dev)
+    # embeddings: robot rows (node 0) and human rows (nodes 1..Nh) of gX, addressed in place as grouped rows
+    _linear_bwd(_rows(gX, 32, 1, n * 32), 32, _rows(sv['a1r'], 64), 64, B, W=g.w_r[2].weight, mask=_rows(sv['X'], 32, 1, n * 32),
+                Gin=_rows(ga_r, 64), dW=G(g.w_r[2].weight), db=G(g.w_r[2].bias), dev=dev)
+    _linear_bwd(_rows(ga_r, 64), 64, _rows(robot, 9), 9, B, mask=_rows(sv['a1r'], 64), dW=G(g.w_r[0].weight), db=G(g.w_r[0].bias), dev=dev)
+    _linear_bwd(_rows(gX, 32, Nh, n * 32, offset=32), 32, _rows(sv['a1h'], 64), 64, B * Nh, W=g.w_h[2].weight,
+                mask=_rows(sv['X'], 32, Nh, n * 32, offset=32), Gin=_rows(ga_h, 64), dW=G(g.w_h[2].weight), db=G(g.w_h[2].bias), dev=dev)
+    _linear_bwd(_rows(ga_h, 64), 64, _rows(humans, 5), 5, B * Nh, mask=_rows(sv['a1h'], 64), dW=G(g.w_h[0].weight),
+                db=G(g.w_h[0].bias), dev=dev)
+
+
+def _grad_buffers(plist, extra, dev):
+    """Zero-filled flat buffer: [gradients of plist | extra floats].  Returns (dict id(p)->view, extra view)."""
+    v = _carve([p.numel() for p in plist] + [extra], dev, zero=True)
+    return {id(p): v[i].view(p.shape) for i, p in enumerate(plist)}, v[len(plist)]
 
 
 class _ValueTrain(torch.autograd.Function):
@@ -43,68 +124,30 @@ class _ValueTrain(torch.autograd.Function):
     def forward(ctx, ve, robot, humans, *params):
         g = ve.graph_model
         robot, humans = ops._check_state(robot, humans)
-        B, Nh = robot.size(0), humans.size(1)
-        n, L, dev = Nh + 1, g.num_layer, robot.device
-        # one flat allocation for every saved activation (views below), instead of ~15 small tensors
-        sizes = [B * 64, B * Nh * 64, B * n * 32, B * n * 32, B * n * n] + [B * n * 32] * (3 * L) + [B * 32, B, B * 32, B * 128, B * 128]
-        flat = torch.empty(sum((x + 3) & ~3 for x in sizes), dtype=torch.float32, device=dev)
-        views, off = [], 0
-        for x in sizes:
-            views.append(flat[off:off + x])
-            off += (x + 3) & ~3
-        sv = dict(a1r=views[0].view(B, 64), a1h=views[1].view(B, Nh, 64), X=views[2].view(B, n, 32), Y=views[3].view(B, n, 32),
-                  A=views[4].view(B, n, n), M=[views[5 + l].view(B, n, 32) for l in range(L)],
-                  Rl=[views[5 + L + l].view(B, n, 32) for l in range(L)], Hl=[views[5 + 2 * L + l].view(B, n, 32) for l in range(L)])
-        E, V, v0, v1, v2 = (views[5 + 3 * L].view(B, 32), views[6 + 3 * L].view(B, 1), views[7 + 3 * L].view(B, 32),
-                            views[8 + 3 * L].view(B, 128), views[9 + 3 * L].view(B, 128))
-        cs = _lib.GraphSave()
-        for k in ('a1r', 'a1h', 'X', 'Y', 'A'):
-            setattr(cs, k, sv[k].data_ptr())
-        for l in range(L):
-            cs.M[l], cs.Rl[l], cs.Hl[l] = sv['M'][l].data_ptr(), sv['Rl'][l].data_ptr(), sv['Hl'][l].data_ptr()
-        lib = _lib.lib()
+        B, dev = robot.size(0), robot.device
+        sv, ex, E, _ = _graph_forward_train(g, robot, humans, [B, B * 32, B * 128, B * 128], want_E=True)
+        V, v0, v1, v2 = ex[0].view(B, 1), ex[1].view(B, 32), ex[2].view(B, 128), ex[3].view(B, 128)
         with torch.cuda.device(dev):
-            rc = lib.rgl_graph_forward_train(_lib.ptr(robot), _lib.ptr(humans), B, Nh, _lib.ptr(ops.packed_graph(g)), L,
-                                             g.flags(), ctypes.byref(cs), None, _lib.ptr(E), _lib.stream_ptr(dev))
-            _lib.check(rc, 'rgl_graph_forward_train')
-            rc = lib.rgl_value_head_train(_lib.ptr(E), B, _lib.ptr(ops.packed_value(ve.value_network, ve._pack_cache)),
-                                          _lib.ptr(V), _lib.ptr(v0), _lib.ptr(v1), _lib.ptr(v2), _lib.stream_ptr(dev))
-            _lib.check(rc, 'rgl_value_head_train')
-        ops._count(2)
+            rc = _lib.lib().rgl_value_head_train(_lib.ptr(E), B, _lib.ptr(ops.packed_value(ve.value_network, ve._pack_cache)),
+                                                 _lib.ptr(V), _lib.ptr(v0), _lib.ptr(v1), _lib.ptr(v2), _lib.stream_ptr(dev))
+        _lib.check(rc, 'rgl_value_head_train')
+        ops._count(1)
         ctx.ve, ctx.sv, ctx.acts = ve, sv, (robot, humans, E, v0, v1, v2)
-        ctx.nparams = len(params)
         return V.clone()
 
     @staticmethod
     def backward(ctx, gV):
         ve, sv = ctx.ve, ctx.sv
-        g = ve.graph_model
+        g, vn = ve.graph_model, ve.value_network
         robot, humans, E, v0, v1, v2 = ctx.acts
-        B, Nh = robot.size(0), humans.size(1)
-        n, L, dev = Nh + 1, g.num_layer, robot.device
-        skip = bool(g.skip_connection)
+        B, n, dev = robot.size(0), humans.size(1) + 1, robot.device
         gV = gV.contiguous().float()
-        vn = ve.value_network
-        plist = list(g.parameters()) + list(vn.parameters())
-        # one zero-filled flat buffer: [all parameter gradients | gH_L], one uninitialised flat buffer for the temporaries
-        psz = [(p.numel() + 3) & ~3 for p in plist]
-        zflat = torch.zeros(sum(psz) + B * n * 32, dtype=torch.float32, device=dev)
-        gp, off = {}, 0
-        for p, sz in zip(plist, psz):
-            gp[id(p)] = zflat[off:off + p.numel()].view(p.shape)
-            off += sz
-        gH0 = zflat[off:].view(B, n, 32)
-        tsz = [B * 128, B * 128, B * 32, B * n * n, B * n * 32, B * n * 32, B * 64, B * Nh * 64] + [B * n * 32] * L
-        tflat = torch.empty(sum((x + 3) & ~3 for x in tsz), dtype=torch.float32, device=dev)
-        tv, off = [], 0
-        for x in tsz:
-            tv.append(tflat[off:off + x])
-            off += (x + 3) & ~3
+        gp, gHflat = _grad_buffers(list(g.parameters()) + list(vn.parameters()), B * n * 32, dev)
         G = lambda p: gp[id(p)]   # noqa: E731
         with torch.cuda.device(dev), torch.no_grad():
-            # ---------------- value head: V = L6(relu(L4(relu(L2(relu(L0(E))))))) ----------------
-            g2, g1, g0 = tv[0].view(B, 128), tv[1].view(B, 128), tv[2].view(B, 32)
-            gH = gH0                                      # gradient w.r.t. H_L: only the robot row is non-zero
+            t = _carve([B * 128, B * 128, B * 32], dev)
+            g2, g1, g0 = t[0].view(B, 128), t[1].view(B, 128), t[2].view(B, 32)
+            gH = gHflat.view(B, n, 32)                    # gradient w.r.t. H_L: only the robot row is non-zero
             _linear_bwd(_rows(gV, 1), 1, _rows(v2, 128), 100, B, W=vn[6].weight, Gin=_rows(g2, 128), dW=G(vn[6].weight), db=G(vn[6].bias), dev=dev)
             _linear_bwd(_rows(g2, 128), 100, _rows(v1, 128), 100, B, W=vn[4].weight, mask=_rows(v2, 128), Gin=_rows(g1, 128),
                         dW=G(vn[4].weight), db=G(vn[4].bias), dev=dev)
@@ -112,47 +155,57 @@ class _ValueTrain(torch.autograd.Function):
                         dW=G(vn[2].weight), db=G(vn[2].bias), dev=dev)
             _linear_bwd(_rows(g0, 32), 32, _rows(E, 32), 32, B, W=vn[0].weight, mask=_rows(v0, 32),
                         Gin=_rows(gH, 32, 1, n * 32), dW=G(vn[0].weight), db=G(vn[0].bias), dev=dev)
-            # ---------------- GCN layers, last to first ----------------
-            gA = tv[3].view(B, n, n)
-            gM = tv[4].view(B, n, 32)
-            lib = _lib.lib()
-            for l in range(L - 1, -1, -1):
-                Hprev = sv['X'] if l == 0 else sv['Hl'][l - 1]
-                _linear_bwd(_rows(gH, 32), 32, _rows(sv['M'][l], 32), 32, B * n, W=g.Ws[l], w_layout=1, mask=_rows(sv['Rl'][l], 32),
-                            Gin=_rows(gM, 32), dW=G(g.Ws[l]), dev=dev)
-                gHp = tv[8 + l].view(B, n, 32)
-                rc = lib.rgl_attn_layer_bwd(_lib.ptr(sv['A']), _lib.ptr(Hprev), _lib.ptr(gM), _lib.ptr(gH), 1 if skip else 0,
-                                            _lib.ptr(gHp), _lib.ptr(gA), 0 if l == L - 1 else 1, B, n, _lib.stream_ptr(dev))
-                _lib.check(rc, 'rgl_attn_layer_bwd')
-                ops._count(1)
-                gH = gHp
-            gX = gH                                         # gradient w.r.t. X from the layer stack
-            # ---------------- similarity ----------------
-            gY = tv[5].view(B, n, 32)
-            rc = lib.rgl_sim_bwd(_lib.ptr(sv['A']), _lib.ptr(gA), _lib.ptr(sv['X']), _lib.ptr(sv['Y']), _lib.ptr(gY), _lib.ptr(gX),
-                                 B, n, _lib.stream_ptr(dev))
-            _lib.check(rc, 'rgl_sim_bwd')
-            ops._count(1)
-            _linear_bwd(_rows(gY, 32), 32, _rows(sv['X'], 32), 32, B * n, W=g.w_a, w_layout=1, Gin=_rows(gX, 32), accumulate=True,
-                        dW=G(g.w_a), dev=dev)
-            # ---------------- embeddings: robot rows (node 0) and human rows (nodes 1..Nh) of gX ----------------
-            ga_r, ga_h = tv[6].view(B, 64), tv[7].view(B * Nh, 64)
-            _linear_bwd(_rows(gX, 32, 1, n * 32), 32, _rows(sv['a1r'], 64), 64, B, W=g.w_r[2].weight, mask=_rows(sv['X'], 32, 1, n * 32),
-                        Gin=_rows(ga_r, 64), dW=G(g.w_r[2].weight), db=G(g.w_r[2].bias), dev=dev)
-            _linear_bwd(_rows(ga_r, 64), 64, _rows(robot, 9), 9, B, mask=_rows(sv['a1r'], 64), dW=G(g.w_r[0].weight), db=G(g.w_r[0].bias), dev=dev)
-            _linear_bwd(_rows(gX, 32, Nh, n * 32, offset=32), 32, _rows(sv['a1h'], 64), 64, B * Nh, W=g.w_h[2].weight,
-                        mask=_rows(sv['X'], 32, Nh, n * 32, offset=32), Gin=_rows(ga_h, 64), dW=G(g.w_h[2].weight), db=G(g.w_h[2].bias), dev=dev)
-            _linear_bwd(_rows(ga_h, 64), 64, _rows(humans, 5), 5, B * Nh, mask=_rows(sv['a1h'], 64), dW=G(g.w_h[0].weight),
-                        db=G(g.w_h[0].bias), dev=dev)
+            _graph_backward(g, sv, robot, humans, gH, G, dev)
         grads = [gp[id(p)] for p in ve._train_params()]
         ctx.sv = ctx.acts = None
         return (None, None, None) + tuple(grads)
 
 
-def native_supported(ve):
-    g = ve.graph_model
-    return ve.kernel_supported() and not g.layerwise_graph
+class _StatePredTrain(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sp, detach, robot, humans, *params):
+        g = sp.graph_model
+        robot, humans = ops._check_state(robot, humans)
+        mblob = ops.packed_motion(sp.human_motion_predictor, sp._pack_cache)
+        sv, _, _, S = _graph_forward_train(g, robot, humans, [], motion_blob=mblob, want_S=True)
+        ctx.sp, ctx.sv, ctx.acts, ctx.detach = sp, sv, (robot, humans), detach
+        return S.clone()
+
+    @staticmethod
+    def backward(ctx, gS):
+        sp, sv, detach = ctx.sp, ctx.sv, ctx.detach
+        g, mp = sp.graph_model, sp.human_motion_predictor
+        robot, humans = ctx.acts
+        B, Nh, dev = robot.size(0), humans.size(1), robot.device
+        n, L = Nh + 1, g.num_layer
+        gS = gS.contiguous().float()
+        plist = list(mp.parameters()) + ([] if detach else list(g.parameters()))
+        gp, gHflat = _grad_buffers(plist, B * n * 32, dev)
+        G = lambda p: gp[id(p)]   # noqa: E731
+        with torch.cuda.device(dev), torch.no_grad():
+            gmh = _carve([B * Nh * 64], dev)[0].view(B * Nh, 64)
+            gH = gHflat.view(B, n, 32)                    # gradient w.r.t. H_L: human rows only (the head drops node 0)
+            HL = sv['Hl'][L - 1]
+            _linear_bwd(_rows(gS, 5), 5, _rows(sv['mh'], 64), 64, B * Nh, W=mp[2].weight, Gin=_rows(gmh, 64), dW=G(mp[2].weight),
+                        db=G(mp[2].bias), dev=dev)
+            _linear_bwd(_rows(gmh, 64), 64, _rows(HL, 32, Nh, n * 32, offset=32), 32, B * Nh, W=None if detach else mp[0].weight,
+                        mask=_rows(sv['mh'], 64), Gin=None if detach else _rows(gH, 32, Nh, n * 32, offset=32),
+                        dW=G(mp[0].weight), db=G(mp[0].bias), dev=dev)
+            if not detach:
+                _graph_backward(g, sv, robot, humans, gH, G, dev)
+        grads = [gp[id(p)] for p in sp._train_params(detach)]
+        ctx.sv = ctx.acts = None
+        return (None, None, None, None) + tuple(grads)
+
+
+def native_supported(module):
+    g = module.graph_model
+    return module.kernel_supported() and not g.layerwise_graph
 
 
 def value_forward_train(ve, robot, humans):
     return _ValueTrain.apply(ve, robot, humans, *ve._train_params())
+
+
+def statepred_forward_train(sp, robot, humans, detach):
+    return _StatePredTrain.apply(sp, detach, robot, humans, *sp._train_params(detach))

@@ -96,3 +96,38 @@ def test_trainer_style_value_update_with_target_network(cuda_device):
         losses.append(float(loss.detach()))
     assert all(torch.isfinite(p).all() for p in ve.parameters())
     assert losses[-1] < losses[0]
+
+
+@pytest.mark.parametrize('nh,B,detach', [(5, 64, False), (5, 100, True), (10, 130, False), (20, 33, False)])
+def test_state_predictor_native_backward(nh, B, detach, cuda_device):
+    """trainer.py:143-149: MSE between predicted and actual next human states; detach=True trains only the motion head."""
+    from relationalgraphlearning_b200.state_predictor import StatePredictor
+    cfg = policy_config()
+    torch.manual_seed(9)
+    g = RGL(cfg, 9, 5)
+    sp = StatePredictor(cfg, g, 0.25)
+    sd_g = {k: v.clone() for k, v in g.state_dict().items()}
+    sd_m = {k: v.clone() for k, v in sp.human_motion_predictor.state_dict().items()}
+    sp.to(cuda_device)
+    robot, humans = synthetic_states(B, nh, seed=4)
+    nxt = humans + 0.25 * torch.randn_like(humans)
+    before = ops.LAUNCHES
+    out = sp((robot.to(cuda_device), humans.to(cuda_device)), None, detach=detach)[1]
+    loss = torch.nn.functional.mse_loss(out, nxt.to(cuda_device))
+    loss.backward()
+    assert ops.LAUNCHES - before >= (3 if detach else 10)
+    pg = {k: v.clone().requires_grad_(True) for k, v in sd_g.items()}
+    pm = {k: v.clone().requires_grad_(True) for k, v in sd_m.items()}
+    H = O.rgl_forward(pg, robot, humans)
+    if detach:
+        H = H.detach()
+    ref = O.mlp(H, pm, '')[:, 1:, :]
+    torch.nn.functional.mse_loss(ref, nxt).backward()
+    assert_close_scaled(out, ref, 1e-5, 'S')
+    for name, p in sp.human_motion_predictor.named_parameters():
+        assert_close_scaled(p.grad, pm[name].grad, 2e-4, 'grad motion ' + name)
+    for name, p in sp.graph_model.named_parameters():
+        if detach:
+            assert p.grad is None
+        else:
+            assert_close_scaled(p.grad, pg[name].grad, 2e-4, 'grad graph ' + name)
