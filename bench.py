@@ -251,13 +251,94 @@ def train_bench(args, rank, world, local):
         dist.destroy_process_group()
 
 
+def plan_bench(args, rank, world, local):
+    """BASELINE configs[2] / [4]: d-step, w-width look-ahead of `--roots` root states per GPU (sharded over ranks, no
+    collective).  Reports root states planned per second and rollout states (value / state-predictor evaluations) per
+    second; CPU leg = the batch-1 oracle tree (oracle/planner_oracle.py) on a bounded number of roots."""
+    import torch.distributed as dist
+    from relationalgraphlearning_b200 import ops
+    from relationalgraphlearning_b200.config import policy_config
+    from relationalgraphlearning_b200.model_predictive_rl import ModelPredictiveRL
+    from relationalgraphlearning_b200.synthetic import synthetic_states
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    E, nh, K, W = args.roots, args.humans, args.steps, max(args.warmup, 3)
+    cfg = policy_config(planning_depth=args.depth, planning_width=args.width, do_action_clip=args.depth > 1 or args.width > 1,
+                        speed_samples=args.speed_samples, rotation_samples=args.rotation_samples)
+    torch.manual_seed(0)
+    pol = ModelPredictiveRL()
+    pol.time_step = 0.25
+    pol.configure(cfg)
+    pol.set_time_step(0.25)
+    pol.set_device(dev)
+    pol.set_phase('test')
+    pol.build_action_space(1.0)
+    pool = [synthetic_states(E, nh, seed=900 + i + 100 * rank, device=dev) for i in range(4)]
+    for i in range(W):
+        pol.predict_batch(*pool[i % 4])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    pol.stat_value_states = pol.stat_sp_states = 0
+    l0 = ops.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        best = pol.predict_batch(*pool[i % 4])
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ms = float(t[0])
+        rollout = (pol.stat_value_states + pol.stat_sp_states) / K
+        out = {'metric': 'model_predictive_rl look-ahead: root states planned/sec (d=%d, w=%d, %d actions, %d humans)' %
+                         (args.depth, args.width, len(pol.action_space), nh),
+               'value': world * E * K / (ms * 1e-3), 'unit': 'root states/s', 'n_gpus': world, 'steps': K, 'warmup': W,
+               'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+               'data': 'synthetic', 'gpu_launches': ops.LAUNCHES - l0,
+               'rollout_states_per_step': rollout, 'rollout_states_per_s': world * rollout * K / (ms * 1e-3),
+               'config': {'workload': 'planner tree d=%d w=%d, %d root states per GPU' % (args.depth, args.width, E),
+                          'parallelism': 'dp%d (root states sharded, no collective)' % world}}
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import planner_oracle as P
+            sd = pol.get_state_dict()
+            cpu = lambda d: {k: v.detach().cpu() for k, v in d.items()}   # noqa: E731
+            orc = P.OraclePlanner(cpu(sd['graph_model1']), cpu(sd['value_network']), cpu(sd['graph_model2']), cpu(sd['motion_predictor']),
+                                  planning_depth=args.depth, planning_width=args.width, do_action_clip=cfg.model_predictive_rl.do_action_clip,
+                                  speed_samples=args.speed_samples, rotation_samples=args.rotation_samples)
+            torch.set_num_threads(1)          # batch-1 forwards: more threads only add overhead
+            r, h = pool[0][0].cpu(), pool[0][1].cpu()
+            t0 = time.perf_counter()
+            nroots = 0
+            while time.perf_counter() - t0 < 10.0 and nroots < E:
+                orc.predict(r[nroots:nroots + 1], h[nroots:nroots + 1])
+                nroots += 1
+            dt = time.perf_counter() - t0
+            out['cpu_baseline'] = {'value': nroots / dt, 'unit': 'root states/s', 'cores': 1, 'kind': 'port',
+                                   'sample': '%d root states through the batch-1 oracle tree (~10 s)' % nroots}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=2000)
     ap.add_argument('--warmup', type=int, default=20)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='graph', choices=['graph', 'value', 'statepred', 'train'])
+    ap.add_argument('--workload', default='graph', choices=['graph', 'value', 'statepred', 'train', 'plan'])
+    ap.add_argument('--roots', type=int, default=1024)
+    ap.add_argument('--depth', type=int, default=2)
+    ap.add_argument('--width', type=int, default=2)
+    ap.add_argument('--speed-samples', type=int, default=2)
+    ap.add_argument('--rotation-samples', type=int, default=5)
     ap.add_argument('--batch', type=int, default=4096)
     ap.add_argument('--humans', type=int, default=5)
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -267,6 +348,11 @@ def main():
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))
+    if args.workload == 'plan':
+        if args.impl == 'reference':
+            print(json.dumps({'impl': 'reference', 'unavailable': 'plan workload: the CPU leg is reported inside the ours arm (cpu_baseline)'}))
+            return
+        return plan_bench(args, rank, world, local)
     if args.workload == 'train':
         if args.impl == 'reference':
             print(json.dumps({'impl': 'reference', 'unavailable': 'train workload: the CPU leg is reported inside the ours arm (cpu_baseline)'}))

@@ -66,6 +66,8 @@ class ModelPredictiveRL(Policy):
         self.traj = None
         self._actions_dev = None          # device copy of the action table (float64 [A,2])
         self._groups_dev = None
+        self.stat_value_states = 0        # states pushed through the value estimator / state predictor (bench counters)
+        self.stat_sp_states = 0
 
     # ------------------------------------------------------------------ configuration (:48-105)
     def configure(self, config):
@@ -208,12 +210,14 @@ class ModelPredictiveRL(Policy):
 
     def _next_humans(self, robot, humans, hb):
         """Predicted humans of every state (independent of the action).  -> [N,Nh,5]"""
+        self.stat_sp_states += robot.size(0)
         if self.linear_state_predictor:
             nh = LinearStatePredictor.linear_motion_approximator(humans)
             return nh.repeat_interleave(hb, dim=0) if hb > 1 else nh
         return self.state_predictor.run(robot, humans, humans_bcast=hb)
 
     def _value(self, robot, humans, hb):
+        self.stat_value_states += robot.size(0)
         return self.value_estimator.run(robot, humans, humans_bcast=hb).view(-1)
 
     def _clip(self, robot, humans, hb, width):
