@@ -187,24 +187,32 @@ def train_bench(args, rank, world, local):
         for i in range(W):
             step(i)
     torch.cuda.synchronize()
-    # the whole step (pack, fused forward, target forward, loss, native backward, all-reduce, fused Adam) is captured
-    # into a CUDA graph of G steps and replayed: no Python / launch overhead inside the timed region
-    G = max(d for d in range(1, 9) if K % d == 0)
-    graph = torch.cuda.CUDAGraph()
+    # single GPU: the whole step (pack, fused forward, target forward, loss, native backward, fused Adam) is captured into a
+    # CUDA graph of G steps and replayed (no Python / launch overhead in the timed region).  With world > 1 the steps run
+    # eagerly: the NCCL all-reduce is issued from Python between backward and the optimizer step.
+    use_graph = world == 1
+    G = max(d for d in range(1, 9) if K % d == 0) if use_graph else 1
     l0 = ops.LAUNCHES
-    with torch.cuda.stream(side):
-        with torch.cuda.graph(graph, stream=side):
-            for i in range(G):
-                loss = step(W + i)
-    launches_per_graph = ops.LAUNCHES - l0
-    graph.replay()
+    if use_graph:
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(graph, stream=side):
+                for i in range(G):
+                    loss = step(W + i)
+        launches_per_graph = ops.LAUNCHES - l0
+        graph.replay()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(K // G):
-        graph.replay()
+    if use_graph:
+        for _ in range(K // G):
+            graph.replay()
+    else:
+        for i in range(K):
+            loss = step(W + i)
+        launches_per_graph = ops.LAUNCHES - l0
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -217,7 +225,8 @@ def train_bench(args, rank, world, local):
         out = {'metric': 'RGL value-net training samples/sec (batch %d per GPU, %d humans)' % (B, nh),
                'value': world * B * K / (ms * 1e-3), 'unit': 'samples/s', 'n_gpus': world, 'steps': K, 'warmup': W,
                'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-               'data': 'synthetic', 'gpu_launches': launches_per_graph * (K // G), 'final_loss': float(loss),
+               'data': 'synthetic', 'gpu_launches': launches_per_graph * (K // G) if use_graph else launches_per_graph, 'final_loss': float(loss),
+               'graph_captured': use_graph,
                'config': {'workload': 'value-net train step B=%d Nh=%d (BASELINE configs[3]): fused fwd+saves, native bwd, Adam' % (B, nh),
                           'grad_allreduce_bytes': red.numel * 4 if world > 1 else 0,
                           'parallelism': 'dp%d, one flat all-reduce per step' % world}}
