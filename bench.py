@@ -285,8 +285,9 @@ def plan_bench(args, rank, world, local):
     pol.set_phase('test')
     pol.build_action_space(1.0)
     pool = [synthetic_states(E, nh, seed=900 + i + 100 * rank, device=dev) for i in range(4)]
+    run = (lambda r, h: pol.predict_batch_graphed(r, h)[0]) if args.plan_graph else pol.predict_batch
     for i in range(W):
-        pol.predict_batch(*pool[i % 4])
+        run(*pool[i % 4])
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -295,7 +296,7 @@ def plan_bench(args, rank, world, local):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(K):
-        best = pol.predict_batch(*pool[i % 4])
+        best = run(*pool[i % 4])
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -344,6 +345,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='graph', choices=['graph', 'value', 'statepred', 'train', 'plan'])
     ap.add_argument('--roots', type=int, default=1024)
+    ap.add_argument('--plan-graph', action='store_true', help='replay the look-ahead from a captured CUDA graph')
     ap.add_argument('--depth', type=int, default=2)
     ap.add_argument('--width', type=int, default=2)
     ap.add_argument('--speed-samples', type=int, default=2)

@@ -68,6 +68,9 @@ class ModelPredictiveRL(Policy):
         self._groups_dev = None
         self.stat_value_states = 0        # states pushed through the value estimator / state predictor (bench counters)
         self.stat_sp_states = 0
+        self.use_cuda_graphs = True       # predict(): replay a captured CUDA graph of the whole look-ahead per (E, Nh) shape
+        self._graphs = {}
+        self._num_groups = 1
 
     # ------------------------------------------------------------------ configuration (:48-105)
     def configure(self, config):
@@ -118,6 +121,7 @@ class ModelPredictiveRL(Policy):
         for model in self.model:
             model.to(device)
         self._actions_dev = None
+        self._graphs = {}
 
     def set_epsilon(self, epsilon):
         self.epsilon = epsilon
@@ -199,6 +203,8 @@ class ModelPredictiveRL(Policy):
             tab = np.array([[a.vx, a.vy] for a in self.action_space], dtype=np.float64)
             self._actions_dev = torch.from_numpy(tab).to(self.device)
             self._groups_dev = torch.tensor(self.action_group_index, dtype=torch.long, device=self.device)
+            self._num_groups = max(self.action_group_index) + 1
+            self._graphs = {}
         return self._actions_dev
 
     # ------------------------------------------------------------------ batched tree
@@ -231,7 +237,7 @@ class ModelPredictiveRL(Policy):
             # walk by descending value (ties: higher index first), keep the first action of each unseen group
             order = (A - 1) - torch.argsort(-vals.flip(1), dim=1, stable=True)
             g = self._groups_dev[order]                                       # group of each visited action
-            G = int(self._groups_dev.max()) + 1
+            G = self._num_groups
             assert width <= G, 'sparse search keeps at most one action per group'
             onehot = torch.nn.functional.one_hot(g, G)
             first = (onehot.cumsum(1) * onehot).sum(2) == 1                   # first visit of its group
@@ -296,6 +302,45 @@ class ModelPredictiveRL(Policy):
             return best_action, dict(value=value, best=best, acts=acts, rew=rew, next_robot=nxt, next_humans=nh, node=node, ret=ret)
         return best_action
 
+    def _refresh_packed_weights(self):
+        """Re-pack any module whose parameters changed (the captured graphs read the packed blobs in place)."""
+        ve = self.value_estimator
+        ops.packed_graph(ve.graph_model)
+        ops.packed_value(ve.value_network, ve._pack_cache)
+        sp = self.state_predictor
+        if getattr(sp, 'trainable', False):
+            ops.packed_graph(sp.graph_model)
+            ops.packed_motion(sp.human_motion_predictor, sp._pack_cache)
+
+    def predict_batch_graphed(self, robot, humans):
+        """predict_batch(..., return_details=True) replayed from a CUDA graph captured once per input shape: the
+        ~10-40 launches of a look-ahead become one cudaGraphLaunch (single-state planning latency, BASELINE C1)."""
+        if self.action_space is None:
+            self.build_action_space(self.v_pref)
+        self._action_table()
+        key = (robot.size(0), humans.size(1), self.planning_depth, self.planning_width, bool(self.do_action_clip),
+               bool(self.sparse_search), float(self.time_step), str(robot.device))
+        self._refresh_packed_weights()
+        entry = self._graphs.get(key)
+        if entry is None:
+            sr, sh = robot.clone(), humans.clone()
+            side = torch.cuda.Stream(robot.device)
+            side.wait_stream(torch.cuda.current_stream(robot.device))
+            with torch.cuda.stream(side):
+                self.predict_batch(sr, sh)                         # warm-up outside capture
+            side.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                best, det = self.predict_batch(sr, sh, return_details=True)
+            entry = (g, sr, sh, best, det)
+            if len(self._graphs) < 64:
+                self._graphs[key] = entry
+        g, sr, sh, best, det = entry
+        sr.copy_(robot)
+        sh.copy_(humans)
+        g.replay()
+        return best, det
+
     # ------------------------------------------------------------------ predict (:192-240)
     def predict(self, state):
         if self.phase is None or self.device is None:
@@ -313,7 +358,10 @@ class ModelPredictiveRL(Policy):
             max_action = self.action_space[np.random.choice(len(self.action_space))]
         else:
             robot, humans = joint_state_to_tensors(state, self.device)
-            best, det = self.predict_batch(robot, humans, return_details=True)
+            if self.use_cuda_graphs:
+                best, det = self.predict_batch_graphed(robot, humans)
+            else:
+                best, det = self.predict_batch(robot, humans, return_details=True)
             b = int(best[0])
             if b < 0:
                 raise ValueError('Value network is not well trained.')

@@ -197,3 +197,29 @@ def test_reference_shaped_helpers(cuda_device):
     assert len(clipped) == 3 and all(isinstance(a, ActionXY) for a in clipped)
     rt, ht = pol.transform(st)
     assert rt.shape == (1, 9) and ht.shape == (5, 5) and rt.device.type == 'cuda'
+
+
+@pytest.mark.gpu
+def test_graphed_predict_equals_eager_and_tracks_weight_updates(cuda_device):
+    g = load_golden('planner_d1_nh5')
+    pol = make_policy(g, cuda_device, planning_depth=2, planning_width=2, do_action_clip=True)
+    pol.build_action_space(1.0)
+    robot, humans = g['robot'][:1].to(cuda_device), g['humans'][:1].to(cuda_device)
+    be, de = pol.predict_batch(robot, humans, return_details=True)
+    for rep in range(3):
+        bg, dg = pol.predict_batch_graphed(robot, humans)
+        assert int(bg[0]) == int(be[0]) and torch.equal(dg['value'], de['value'])
+    # other inputs through the same captured graph
+    r2, h2 = g['robot'][4:5].to(cuda_device), g['humans'][4:5].to(cuda_device)
+    b2, d2 = pol.predict_batch_graphed(r2, h2)
+    e2, f2 = pol.predict_batch(r2, h2, return_details=True)
+    assert int(b2[0]) == int(e2[0]) and torch.equal(d2['value'], f2['value'])
+    # a parameter update must be visible to the replayed graph (packed blobs are refreshed in place)
+    with torch.no_grad():
+        pol.value_estimator.value_network[6].bias.add_(0.25)
+    b3, d3 = pol.predict_batch_graphed(r2, h2)
+    e3, f3 = pol.predict_batch(r2, h2, return_details=True)
+    assert torch.equal(d3['value'], f3['value']) and not torch.equal(d3['value'], d2['value'])
+    # predict() uses the graphed path and still builds the trajectory
+    a = pol.predict(joint_state(g['robot'], g['humans'], 0))
+    assert a == pol.action_space[int(be[0])] and pol.traj[0][1] == a
