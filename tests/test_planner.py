@@ -214,12 +214,13 @@ def test_graphed_predict_equals_eager_and_tracks_weight_updates(cuda_device):
     b2, d2 = pol.predict_batch_graphed(r2, h2)
     e2, f2 = pol.predict_batch(r2, h2, return_details=True)
     assert int(b2[0]) == int(e2[0]) and torch.equal(d2['value'], f2['value'])
+    v2 = d2['value'].clone()          # graph outputs are static tensors: the next replay overwrites them
     # a parameter update must be visible to the replayed graph (packed blobs are refreshed in place)
     with torch.no_grad():
         pol.value_estimator.value_network[6].bias.add_(0.25)
     b3, d3 = pol.predict_batch_graphed(r2, h2)
     e3, f3 = pol.predict_batch(r2, h2, return_details=True)
-    assert torch.equal(d3['value'], f3['value']) and not torch.equal(d3['value'], d2['value'])
+    assert torch.equal(d3['value'], f3['value']) and not torch.equal(d3['value'], v2)
     # predict() uses the graphed path and still builds the trajectory
     a = pol.predict(joint_state(g['robot'], g['humans'], 0))
     assert a == pol.action_space[int(be[0])] and pol.traj[0][1] == a
