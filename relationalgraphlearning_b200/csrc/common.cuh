@@ -16,17 +16,20 @@ constexpr int LDX = XD + 4;             // padded smem row stride (floats): 36 =
 // ---- packed graph blob (floats), all matrices k-major W[k][N] -----------------------------------
 // (PyTorch Linear stores [out,in]; the pack kernel transposes.  w_a / Ws are used as X @ W and are
 //  already [k][N].)
+constexpr int LDW = XD + 8;                     // row stride of the 32-column weight matrices: 40 = 8 mod 32, so the
+                                                // mma B-fragment pattern (row k0+t, column n0+g) hits 32 distinct banks;
+                                                // LDS.128 users only need a multiple of 4
 constexpr int G_WR0 = 0;                       // [9][64]
 constexpr int G_BR0 = G_WR0 + RD * HID;        // [64]
-constexpr int G_WR1 = G_BR0 + HID;             // [64][32]
-constexpr int G_BR1 = G_WR1 + HID * XD;        // [32]
+constexpr int G_WR1 = G_BR0 + HID;             // [64][LDW]
+constexpr int G_BR1 = G_WR1 + HID * LDW;       // [32]
 constexpr int G_WH0 = G_BR1 + XD;              // [5][64]
 constexpr int G_BH0 = G_WH0 + HD * HID;        // [64]
-constexpr int G_WH1 = G_BH0 + HID;             // [64][32]
-constexpr int G_BH1 = G_WH1 + HID * XD;        // [32]
-constexpr int G_WA  = G_BH1 + XD;              // [32][32]
-constexpr int G_WS  = G_WA + XD * XD;          // num_layer x [32][32]
-__host__ __device__ constexpr int graph_floats(int L) { return G_WS + L * XD * XD; }
+constexpr int G_WH1 = G_BH0 + HID;             // [64][LDW]
+constexpr int G_BH1 = G_WH1 + HID * LDW;       // [32]
+constexpr int G_WA  = G_BH1 + XD;              // [32][LDW]
+constexpr int G_WS  = G_WA + XD * LDW;         // num_layer x [32][LDW]
+__host__ __device__ constexpr int graph_floats(int L) { return G_WS + L * XD * LDW; }
 
 // ---- packed value blob: mlp(32,[32,100,100,1]); hidden 100 padded to 128 columns with zeros -----
 constexpr int VH  = RGL_VALUE_HIDDEN;   // 100
@@ -49,7 +52,7 @@ constexpr int M_W1 = M_B0 + MH;                // [5][64]  (PyTorch layout: one 
 constexpr int M_B1 = M_W1 + HD * MH;           // [8] (5 used)
 constexpr int MOTION_FLOATS = M_B1 + 8;
 
-static_assert(graph_floats(2) == 8256, "graph parameter count (SURVEY.md 2b)");
+static_assert(graph_floats(2) - (2 * HID + 3 * XD) * (LDW - XD) == 8256, "graph parameter count (SURVEY.md 2b) + row padding");
 static_assert(graph_floats(RGL_MAX_LAYERS) % 4 == 0 && VALUE_FLOATS % 4 == 0 && MOTION_FLOATS % 4 == 0, "16B sections");
 
 // ---- PTX: mbarrier + TMA bulk copy (cp.async.bulk -> SASS UBLKCP) ------------------------------------
@@ -179,6 +182,77 @@ __device__ __forceinline__ void tile_gemm_pf(float (&acc)[RT][NC4 * 4], const fl
             tile_fma<RT, NC4>(acc, xb, wb);
         }
     }
+}
+
+
+// ---- tensor-core path: legacy warp-level mma.sync (SASS HMMA) with a 3xTF32 split --------------------------------
+// fp32 operands are split x = hi + lo with hi = x truncated to a tf32 mantissa (one LOP3) and lo = x - hi (exact, one
+// FADD; the tensor core ignores its low 13 bits); D += lo*Bhi + hi*Blo + hi*Bhi recovers fp32-level products
+// (measured 4e-7 relative error on a K=32 dot of O(20) activations, tools/mma_peak.cu) with fp32 accumulation.
+// Measured mma.sync m16n8k8 TF32 rate on this B200: 478 MAC/clk/SM (tcgen05 is 4x that; round-2 target).
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
+// Warp GEMM on tensor cores: acc[mt][nt][.] += X[32 rows][8*KS] * W[8*KS][32].
+//   x: first of the warp's 32 rows (row-major, stride LDX); w: k-major weights, stride LDW (= 8 mod 32: conflict-free
+//   B-fragment loads); accumulator fragment (m16n8): [0],[1] = row g, cols 2t,2t+1; [2],[3] = row g+8 (g = lane>>2, t = lane&3)
+template <int KS>
+__device__ __forceinline__ void mma_gemm_3xtf32(float (&acc)[2][4][4], const float* __restrict__ x, const float* __restrict__ w, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+        uint32_t ahi[2][4], alo[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            const float* xr = x + (mt * 16 + g) * LDX + ks * 8 + t;
+            split_tf32(xr[0], ahi[mt][0], alo[mt][0]);
+            split_tf32(xr[8 * LDX], ahi[mt][1], alo[mt][1]);
+            split_tf32(xr[4], ahi[mt][2], alo[mt][2]);
+            split_tf32(xr[8 * LDX + 4], ahi[mt][3], alo[mt][3]);
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            uint32_t bh0, bl0, bh1, bl1;
+            split_tf32(w[(ks * 8 + t) * LDW + nt * 8 + g], bh0, bl0);
+            split_tf32(w[(ks * 8 + t + 4) * LDW + nt * 8 + g], bh1, bl1);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                mma_tf32(acc[mt][nt], alo[mt], bh0, bh1);       // small terms first
+                mma_tf32(acc[mt][nt], ahi[mt], bl0, bl1);
+                mma_tf32(acc[mt][nt], ahi[mt], bh0, bh1);
+            }
+        }
+    }
+}
+// accumulator-fragment helpers (base = first of the warp's 32 rows, stride LDX)
+__device__ __forceinline__ void cfrag_fill(float (&acc)[2][4][4], const float* bias, int lane) {
+    const int t = lane & 3;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+        const float b0 = bias ? bias[nt * 8 + 2 * t] : 0.f, b1 = bias ? bias[nt * 8 + 2 * t + 1] : 0.f;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) { acc[mt][nt][0] = b0; acc[mt][nt][1] = b1; acc[mt][nt][2] = b0; acc[mt][nt][3] = b1; }
+    }
+}
+template <bool RELU>
+__device__ __forceinline__ void cfrag_store(float* base, const float (&acc)[2][4][4], int lane) {
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            float2 lo = make_float2(acc[mt][nt][0], acc[mt][nt][1]), hi = make_float2(acc[mt][nt][2], acc[mt][nt][3]);
+            if (RELU) { lo.x = fmaxf(lo.x, 0.f); lo.y = fmaxf(lo.y, 0.f); hi.x = fmaxf(hi.x, 0.f); hi.y = fmaxf(hi.y, 0.f); }
+            *reinterpret_cast<float2*>(base + (mt * 16 + g) * LDX + nt * 8 + 2 * t) = lo;
+            *reinterpret_cast<float2*>(base + (mt * 16 + g + 8) * LDX + nt * 8 + 2 * t) = hi;
+        }
 }
 
 // Same tile, x read with scalar loads (tiny K not a multiple of 4: the raw 9- / 5-float states).

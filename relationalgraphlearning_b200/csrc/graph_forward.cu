@@ -87,9 +87,10 @@ __device__ __forceinline__ void bias_tile(float (&acc)[RT][8], const float* b, i
 
 // launch bounds: RPT > 0 (row-per-thread per-state phases, RT = 4) runs n warps per CTA and two CTAs per SM when
 // shared memory allows (N = 6); the other variants run one CTA per SM.
-template <int TS, int RT, int N, int RPT>
+template <int TS, int RT, int N, int RPT, bool MMA = false>
 __global__ void __launch_bounds__(RPT > 0 ? N * 32 : (N == 6 ? 384 : 512), (RPT > 0 && N <= 8) ? 2 : 1)
 graph_forward_kernel(const GraphArgs a) {
+    static_assert(!MMA || RT == 4, "the tensor-core GEMMs work on 32-row blocks");
     constexpr int RB = 8 * RT;
     static_assert(TS % RB == 0, "a row block must not straddle two agents");
     extern __shared__ __align__(128) float smem[];
@@ -184,9 +185,30 @@ graph_forward_kernel(const GraphArgs a) {
 #pragma unroll
                 for (int q = 0; q < RT; ++q) xrow[q] = rawH + ((sb + rg + 8 * q) * Nh + (agent - 1)) * HD;
             }
+            float* scr = YB + (r0 + rg) * LDX;       // this warp's own rows of YB double as the hidden scratch
+            float* xo = XB + (r0 + rg) * LDX;
+            if constexpr (MMA) {
+                // layer 2 (64 -> 32) and Y = X w_a on the tensor cores (3xTF32); layer 1 (K = 5 / 9) stays on the FMA pipe
+                float macc[2][4][4];
+                cfrag_fill(macc, B1, lane);
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+                    float acc1[RT][8];
+                    bias_tile<RT>(acc1, B0 + half * 32, cg);
+                    tile_gemm_smallk<RT, 2>(acc1, xrow, W0 + half * 32 + cg * 4, HID, K0);
+                    store_tile_relu<RT>(scr, cg, acc1);
+                    __syncwarp();
+                    mma_gemm_3xtf32<4>(macc, YB + r0 * LDX, W1 + half * 32 * LDW, lane);
+                    __syncwarp();
+                }
+                cfrag_store<true>(XB + r0 * LDX, macc, lane);
+                __syncwarp();
+                cfrag_fill(macc, nullptr, lane);
+                mma_gemm_3xtf32<4>(macc, XB + r0 * LDX, gw + G_WA, lane);
+                cfrag_store<false>(YB + r0 * LDX, macc, lane);
+            } else {
             float acc2[RT][8];
             bias_tile<RT>(acc2, B1, cg);
-            float* scr = YB + (r0 + rg) * LDX;       // this warp's own rows of YB double as the hidden scratch
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {
                 float acc1[RT][8];
@@ -209,16 +231,16 @@ graph_forward_kernel(const GraphArgs a) {
                     }
                 }
                 __syncwarp();
-                tile_gemm_pf<RT, 2, 32>(acc2, scr, LDX, W1 + half * 32 * XD + cg * 4, XD);
+                tile_gemm_pf<RT, 2, 32>(acc2, scr, LDX, W1 + half * 32 * LDW + cg * 4, LDW);
                 __syncwarp();
             }
-            float* xo = XB + (r0 + rg) * LDX;
             store_tile_relu<RT>(xo, cg, acc2);
             __syncwarp();
             float accy[RT][8];
             zero_tile<RT>(accy);
-            tile_gemm_pf<RT, 2, XD>(accy, xo, LDX, gw + G_WA + cg * 4, XD);
+            tile_gemm_pf<RT, 2, XD>(accy, xo, LDX, gw + G_WA + cg * 4, LDW);
             store_tile<RT>(scr, cg, accy);
+            }
         }
         __syncthreads();
 
@@ -247,10 +269,17 @@ graph_forward_kernel(const GraphArgs a) {
             if (l == 0 || layerwise) {
                 if (l > 0) {                              // Y = H w_a for the layerwise graph
                     for (int rb = warp; rb * RB < rows; rb += nwarps) {
-                        float accy[RT][8];
-                        zero_tile<RT>(accy);
-                        tile_gemm_pf<RT, 2, XD>(accy, XB + (rb * RB + rg) * LDX, LDX, gw + G_WA + cg * 4, XD);
-                        store_tile<RT>(YB + (rb * RB + rg) * LDX, cg, accy);
+                        if constexpr (MMA) {
+                            float macc[2][4][4];
+                            cfrag_fill(macc, nullptr, lane);
+                            mma_gemm_3xtf32<4>(macc, XB + rb * RB * LDX, gw + G_WA, lane);
+                            cfrag_store<false>(YB + rb * RB * LDX, macc, lane);
+                        } else {
+                            float accy[RT][8];
+                            zero_tile<RT>(accy);
+                            tile_gemm_pf<RT, 2, XD>(accy, XB + (rb * RB + rg) * LDX, LDX, gw + G_WA + cg * 4, LDW);
+                            store_tile<RT>(YB + (rb * RB + rg) * LDX, cg, accy);
+                        }
                     }
                     __syncthreads();
                 }
@@ -522,10 +551,38 @@ graph_forward_kernel(const GraphArgs a) {
             for (int rb = warp; rb * RB < rows; rb += nwarps) {
                 const int r0 = rb * RB;
                 const int agent = r0 / TS;
+                float* xo = XB + (r0 + rg) * LDX;
+                if constexpr (MMA) {
+                    float macc[2][4][4];
+                    cfrag_fill(macc, nullptr, lane);
+                    mma_gemm_3xtf32<4>(macc, YB + r0 * LDX, gw + G_WS + l * XD * LDW, lane);
+                    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            const int rr = r0 + mt * 16 + g + 8 * hh;        // node row; s = its state inside the tile
+                            const int s = rr - agent * TS;
+#pragma unroll
+                            for (int nt = 0; nt < 4; ++nt) {
+                                float2 v = make_float2(fmaxf(macc[mt][nt][2 * hh], 0.f), fmaxf(macc[mt][nt][2 * hh + 1], 0.f));
+                                float* p = XB + rr * LDX + nt * 8 + 2 * t;
+                                if (skip) {
+                                    const float2 h = *reinterpret_cast<const float2*>(p);
+                                    v.x += h.x; v.y += h.y;
+                                }
+                                *reinterpret_cast<float2*>(p) = v;
+                                if (last && s < cnt) {
+                                    const size_t gs = (size_t)(s0 + s);
+                                    if (a.H) *reinterpret_cast<float2*>(a.H + (gs * n + agent) * XD + nt * 8 + 2 * t) = v;
+                                    if (a.E && agent == 0) *reinterpret_cast<float2*>(a.E + gs * XD + nt * 8 + 2 * t) = v;
+                                }
+                            }
+                        }
+                } else {
                 float acc[RT][8];
                 zero_tile<RT>(acc);
-                tile_gemm_pf<RT, 2, XD>(acc, YB + (r0 + rg) * LDX, LDX, gw + G_WS + l * XD * XD + cg * 4, XD);
-                float* xo = XB + (r0 + rg) * LDX;
+                tile_gemm_pf<RT, 2, XD>(acc, YB + (r0 + rg) * LDX, LDX, gw + G_WS + l * XD * LDW + cg * 4, LDW);
 #pragma unroll
                 for (int q = 0; q < RT; ++q) {
                     const int s = r0 + rg + 8 * q - agent * TS;
@@ -549,6 +606,7 @@ graph_forward_kernel(const GraphArgs a) {
                             if (a.E && agent == 0) *reinterpret_cast<float4*>(a.E + gs * XD + cg * 4 + 16 * m) = v;
                         }
                     }
+                }
                 }
                 // ---- state-predictor head on human rows: S = W1 relu(W0 h + b0) + b1 (32 -> 64 -> 5) ----
                 if (last && a.S != nullptr && agent >= 1) {
@@ -620,7 +678,7 @@ static size_t graph_smem_bytes(int TS, int Nh, int L, bool motion, bool ctn) {
     return fl * sizeof(float);
 }
 
-template <int TS, int RT, int N, int RPT>
+template <int TS, int RT, int N, int RPT, bool MMA = false>
 static cudaError_t launch_graph(const GraphArgs& a, int num_sms, size_t max_smem, cudaStream_t st) {
     const int n = a.Nh + 1;
     const size_t smem = graph_smem_bytes(TS, a.Nh, a.L, a.mw != nullptr, N > 0);
@@ -632,7 +690,7 @@ static cudaError_t launch_graph(const GraphArgs& a, int num_sms, size_t max_smem
     const int nwarps = nrb < cap ? nrb : cap;
     static bool attr_set = false;     // benign race: idempotent
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(graph_forward_kernel<TS, RT, N, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
+        cudaError_t e = cudaFuncSetAttribute(graph_forward_kernel<TS, RT, N, RPT, MMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -641,7 +699,7 @@ static cudaError_t launch_graph(const GraphArgs& a, int num_sms, size_t max_smem
     const int max_cta = (RPT > 0 && N <= 8) ? 2 : 1;          // matches the kernel's __launch_bounds__ (register budget)
     if (per_sm > max_cta) per_sm = max_cta;
     const int grid = b.ntiles < num_sms * per_sm ? b.ntiles : num_sms * per_sm;
-    graph_forward_kernel<TS, RT, N, RPT><<<grid, nwarps * 32, smem, st>>>(b);
+    graph_forward_kernel<TS, RT, N, RPT, MMA><<<grid, nwarps * 32, smem, st>>>(b);
     return cudaGetLastError();
 }
 
@@ -654,8 +712,12 @@ static cudaError_t dispatch_tile(const GraphArgs& a, int num_sms, size_t max_sme
         if constexpr (N == 6) {
             // large batches: 32-row register tiles + 2 rows per thread in the per-state phases (least shared-memory
             // traffic per FFMA), two 6-warp CTAs per SM; up to one wave of tiles: 16-row tiles, 12 warps per CTA
+            // RGL_GRAPH_VARIANT (debug/experiments): '2' = 16-row FFMA tiles, '4' = 32-row FFMA tiles, 'm' = 32-row tiles with
+            // the shared-weight GEMMs on the tensor cores (mma.sync 3xTF32)
             static const char* force = getenv("RGL_GRAPH_VARIANT");
-            const bool big = force ? (force[0] == '4') : (tiles32 > num_sms || (a.flags & RGL_FLAG_THROUGHPUT));
+            const bool big = force ? (force[0] != '2') : (tiles32 > num_sms || (a.flags & RGL_FLAG_THROUGHPUT));
+            const bool mma = force ? (force[0] == 'm') : false;
+            if (big && mma && !a.save) return launch_graph<32, 4, 6, 2, true>(a, num_sms, max_smem, st);
             if (big) return launch_graph<32, 4, 6, 2>(a, num_sms, max_smem, st);
         }
         return launch_graph<32, 2, N, 0>(a, num_sms, max_smem, st);

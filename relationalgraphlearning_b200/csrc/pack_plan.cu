@@ -15,18 +15,26 @@ __device__ __forceinline__ void pack_copy(float* dst, const float* src, int N, i
     for (int idx = t; idx < Np; idx += nt) dst[idx] = idx < N ? src[idx] : 0.f;
 }
 
+// dst[k*Np + n] = src[k*N + n] (already k-major), padded columns zero
+__device__ __forceinline__ void pack_rows(float* dst, const float* src, int K, int N, int Np, int t, int nt) {
+    for (int idx = t; idx < K * Np; idx += nt) {
+        const int k = idx / Np, n = idx - k * Np;
+        dst[idx] = n < N ? src[k * N + n] : 0.f;
+    }
+}
+
 __global__ void pack_graph_kernel(RglGraphParams p, float* out) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
     pack_linear_T(out + G_WR0, p.wr0_w, HID, RD, HID, t, nt);
     pack_copy(out + G_BR0, p.wr0_b, HID, HID, t, nt);
-    pack_linear_T(out + G_WR1, p.wr1_w, XD, HID, XD, t, nt);
+    pack_linear_T(out + G_WR1, p.wr1_w, XD, HID, LDW, t, nt);
     pack_copy(out + G_BR1, p.wr1_b, XD, XD, t, nt);
     pack_linear_T(out + G_WH0, p.wh0_w, HID, HD, HID, t, nt);
     pack_copy(out + G_BH0, p.wh0_b, HID, HID, t, nt);
-    pack_linear_T(out + G_WH1, p.wh1_w, XD, HID, XD, t, nt);
+    pack_linear_T(out + G_WH1, p.wh1_w, XD, HID, LDW, t, nt);
     pack_copy(out + G_BH1, p.wh1_b, XD, XD, t, nt);
-    pack_copy(out + G_WA, p.w_a, XD * XD, XD * XD, t, nt);
-    for (int l = 0; l < p.num_layer; ++l) pack_copy(out + G_WS + l * XD * XD, p.Ws[l], XD * XD, XD * XD, t, nt);
+    pack_rows(out + G_WA, p.w_a, XD, XD, LDW, t, nt);
+    for (int l = 0; l < p.num_layer; ++l) pack_rows(out + G_WS + l * XD * LDW, p.Ws[l], XD, XD, LDW, t, nt);
 }
 
 __global__ void pack_value_kernel(RglValueParams p, float* out) {
