@@ -48,6 +48,8 @@ extern "C" {
 /* flags for the graph kernels */
 #define RGL_FLAG_SKIP       1         /* config.gcn.skip_connection  (graph_model.py:126-127) */
 #define RGL_FLAG_LAYERWISE  2         /* config.gcn.layerwise_graph  (graph_model.py:120-122) */
+#define RGL_FLAG_FP32_FMA   8         /* numerics: keep every GEMM on the fp32 FMA pipe (no 3xTF32 tensor-core split;
+                                         the tensor path agrees with fp32 to ~3e-6 relative, the FMA path to ~3e-7) */
 #define RGL_FLAG_THROUGHPUT 4         /* scheduling hint: the caller keeps several independent launches in flight
                                          (multi-stream serving); prefer the two-CTAs-per-SM kernel variant */
 

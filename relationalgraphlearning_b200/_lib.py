@@ -15,6 +15,7 @@ MAX_LAYERS = 4
 FLAG_SKIP = 1
 FLAG_LAYERWISE = 2
 FLAG_THROUGHPUT = 4
+FLAG_FP32_FMA = 8
 
 c_float_p = ctypes.c_void_p
 

@@ -78,7 +78,7 @@ int rgl_graph_forward(const float* robot, const float* humans, int B, int Nh, in
     if (B < 0 || humans_bcast < 1) return fail(RGL_EINVAL, "rgl_graph_forward: bad batch / humans_bcast");
     if (Nh < 1 || Nh > RGL_MAX_HUMANS) return fail(RGL_EUNSUPPORTED, "rgl_graph_forward: human count outside [1,31]");
     if (num_layer < 1 || num_layer > RGL_MAX_LAYERS) return fail(RGL_EUNSUPPORTED, "rgl_graph_forward: num_layer out of range");
-    if (flags & ~(RGL_FLAG_SKIP | RGL_FLAG_LAYERWISE | RGL_FLAG_THROUGHPUT)) return fail(RGL_EINVAL, "rgl_graph_forward: unknown flag");
+    if (flags & ~(RGL_FLAG_SKIP | RGL_FLAG_LAYERWISE | RGL_FLAG_THROUGHPUT | RGL_FLAG_FP32_FMA)) return fail(RGL_EINVAL, "rgl_graph_forward: unknown flag");
     if (!aligned16(graph_packed) || (motion_packed && !aligned16(motion_packed)))
         return fail(RGL_EALIGN, "rgl_graph_forward: packed weights must be 16-byte aligned");
     if ((H && !aligned16(H)) || (E && !aligned16(E))) return fail(RGL_EALIGN, "rgl_graph_forward: H/E must be 16-byte aligned");

@@ -186,8 +186,8 @@ __device__ __forceinline__ void tile_gemm_pf(float (&acc)[RT][NC4 * 4], const fl
 
 
 // ---- tensor-core path: legacy warp-level mma.sync (SASS HMMA) with a 3xTF32 split --------------------------------
-// fp32 operands are split x = hi + lo with hi = x truncated to a tf32 mantissa (one LOP3) and lo = x - hi (exact, one
-// FADD; the tensor core ignores its low 13 bits); D += lo*Bhi + hi*Blo + hi*Bhi recovers fp32-level products
+// fp32 operands are split x = hi + lo with hi = x rounded to a tf32 mantissa and lo = x - hi (exact in fp32), itself
+// rounded to tf32; D += lo*Bhi + hi*Blo + hi*Bhi recovers fp32-level products
 // (measured 4e-7 relative error on a K=32 dot of O(20) activations, tools/mma_peak.cu) with fp32 accumulation.
 // Measured mma.sync m16n8k8 TF32 rate on this B200: 478 MAC/clk/SM (tcgen05 is 4x that; round-2 target).
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -196,21 +196,23 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-    hi = __float_as_uint(x) & 0xffffe000u;
-    lo = __float_as_uint(x - __uint_as_float(hi));
+    // round-to-nearest on both parts (integer add of half a tf32 ulp before the low 13 bits are dropped): truncation
+    // would bias every product the same way and the error would grow linearly in K (measured 2.5e-6 vs 3e-7 relative)
+    hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi)) + 0x1000u;       // the tensor core ignores the low 13 bits
 }
 
-// Warp GEMM on tensor cores: acc[mt][nt][.] += X[32 rows][8*KS] * W[8*KS][32].
-//   x: first of the warp's 32 rows (row-major, stride LDX); w: k-major weights, stride LDW (= 8 mod 32: conflict-free
+// Warp GEMM on tensor cores: acc[mt][nt][.] += X[16*MT rows][8*KS] * W[8*KS][32].
+//   x: first of the warp's 16*MT rows (row-major, stride LDX); w: k-major weights, stride LDW (= 8 mod 32: conflict-free
 //   B-fragment loads); accumulator fragment (m16n8): [0],[1] = row g, cols 2t,2t+1; [2],[3] = row g+8 (g = lane>>2, t = lane&3)
-template <int KS>
-__device__ __forceinline__ void mma_gemm_3xtf32(float (&acc)[2][4][4], const float* __restrict__ x, const float* __restrict__ w, int lane) {
+template <int KS, int MT>
+__device__ __forceinline__ void mma_gemm_3xtf32(float (&acc)[MT][4][4], const float* __restrict__ x, const float* __restrict__ w, int lane) {
     const int g = lane >> 2, t = lane & 3;
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
-        uint32_t ahi[2][4], alo[2][4];
+        uint32_t ahi[MT][4], alo[MT][4];
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
+        for (int mt = 0; mt < MT; ++mt) {
             const float* xr = x + (mt * 16 + g) * LDX + ks * 8 + t;
             split_tf32(xr[0], ahi[mt][0], alo[mt][0]);
             split_tf32(xr[8 * LDX], ahi[mt][1], alo[mt][1]);
@@ -223,7 +225,7 @@ __device__ __forceinline__ void mma_gemm_3xtf32(float (&acc)[2][4][4], const flo
             split_tf32(w[(ks * 8 + t) * LDW + nt * 8 + g], bh0, bl0);
             split_tf32(w[(ks * 8 + t + 4) * LDW + nt * 8 + g], bh1, bl1);
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
+            for (int mt = 0; mt < MT; ++mt) {
                 mma_tf32(acc[mt][nt], alo[mt], bh0, bh1);       // small terms first
                 mma_tf32(acc[mt][nt], ahi[mt], bl0, bl1);
                 mma_tf32(acc[mt][nt], ahi[mt], bh0, bh1);
@@ -232,20 +234,21 @@ __device__ __forceinline__ void mma_gemm_3xtf32(float (&acc)[2][4][4], const flo
     }
 }
 // accumulator-fragment helpers (base = first of the warp's 32 rows, stride LDX)
-__device__ __forceinline__ void cfrag_fill(float (&acc)[2][4][4], const float* bias, int lane) {
+template <int MT>
+__device__ __forceinline__ void cfrag_fill(float (&acc)[MT][4][4], const float* bias, int lane) {
     const int t = lane & 3;
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
         const float b0 = bias ? bias[nt * 8 + 2 * t] : 0.f, b1 = bias ? bias[nt * 8 + 2 * t + 1] : 0.f;
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) { acc[mt][nt][0] = b0; acc[mt][nt][1] = b1; acc[mt][nt][2] = b0; acc[mt][nt][3] = b1; }
+        for (int mt = 0; mt < MT; ++mt) { acc[mt][nt][0] = b0; acc[mt][nt][1] = b1; acc[mt][nt][2] = b0; acc[mt][nt][3] = b1; }
     }
 }
-template <bool RELU>
-__device__ __forceinline__ void cfrag_store(float* base, const float (&acc)[2][4][4], int lane) {
+template <bool RELU, int MT>
+__device__ __forceinline__ void cfrag_store(float* base, const float (&acc)[MT][4][4], int lane) {
     const int g = lane >> 2, t = lane & 3;
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
             float2 lo = make_float2(acc[mt][nt][0], acc[mt][nt][1]), hi = make_float2(acc[mt][nt][2], acc[mt][nt][3]);

@@ -90,7 +90,7 @@ __device__ __forceinline__ void bias_tile(float (&acc)[RT][8], const float* b, i
 template <int TS, int RT, int N, int RPT, bool MMA = false>
 __global__ void __launch_bounds__(RPT > 0 ? N * 32 : (N == 6 ? 384 : 512), (RPT > 0 && N <= 8) ? 2 : 1)
 graph_forward_kernel(const GraphArgs a) {
-    static_assert(!MMA || RT == 4, "the tensor-core GEMMs work on 32-row blocks");
+    constexpr int MT = RT / 2;                // 16-row m-tiles per warp row block on the tensor-core path
     constexpr int RB = 8 * RT;
     static_assert(TS % RB == 0, "a row block must not straddle two agents");
     extern __shared__ __align__(128) float smem[];
@@ -189,8 +189,8 @@ graph_forward_kernel(const GraphArgs a) {
             float* xo = XB + (r0 + rg) * LDX;
             if constexpr (MMA) {
                 // layer 2 (64 -> 32) and Y = X w_a on the tensor cores (3xTF32); layer 1 (K = 5 / 9) stays on the FMA pipe
-                float macc[2][4][4];
-                cfrag_fill(macc, B1, lane);
+                float macc[MT][4][4];
+                cfrag_fill<MT>(macc, B1, lane);
 #pragma unroll 1
                 for (int half = 0; half < 2; ++half) {
                     float acc1[RT][8];
@@ -198,14 +198,14 @@ graph_forward_kernel(const GraphArgs a) {
                     tile_gemm_smallk<RT, 2>(acc1, xrow, W0 + half * 32 + cg * 4, HID, K0);
                     store_tile_relu<RT>(scr, cg, acc1);
                     __syncwarp();
-                    mma_gemm_3xtf32<4>(macc, YB + r0 * LDX, W1 + half * 32 * LDW, lane);
+                    mma_gemm_3xtf32<4, MT>(macc, YB + r0 * LDX, W1 + half * 32 * LDW, lane);
                     __syncwarp();
                 }
-                cfrag_store<true>(XB + r0 * LDX, macc, lane);
+                cfrag_store<true, MT>(XB + r0 * LDX, macc, lane);
                 __syncwarp();
-                cfrag_fill(macc, nullptr, lane);
-                mma_gemm_3xtf32<4>(macc, XB + r0 * LDX, gw + G_WA, lane);
-                cfrag_store<false>(YB + r0 * LDX, macc, lane);
+                cfrag_fill<MT>(macc, nullptr, lane);
+                mma_gemm_3xtf32<4, MT>(macc, XB + r0 * LDX, gw + G_WA, lane);
+                cfrag_store<false, MT>(YB + r0 * LDX, macc, lane);
             } else {
             float acc2[RT][8];
             bias_tile<RT>(acc2, B1, cg);
@@ -270,10 +270,10 @@ graph_forward_kernel(const GraphArgs a) {
                 if (l > 0) {                              // Y = H w_a for the layerwise graph
                     for (int rb = warp; rb * RB < rows; rb += nwarps) {
                         if constexpr (MMA) {
-                            float macc[2][4][4];
-                            cfrag_fill(macc, nullptr, lane);
-                            mma_gemm_3xtf32<4>(macc, XB + rb * RB * LDX, gw + G_WA, lane);
-                            cfrag_store<false>(YB + rb * RB * LDX, macc, lane);
+                            float macc[MT][4][4];
+                            cfrag_fill<MT>(macc, nullptr, lane);
+                            mma_gemm_3xtf32<4, MT>(macc, XB + rb * RB * LDX, gw + G_WA, lane);
+                            cfrag_store<false, MT>(YB + rb * RB * LDX, macc, lane);
                         } else {
                             float accy[RT][8];
                             zero_tile<RT>(accy);
@@ -553,12 +553,12 @@ graph_forward_kernel(const GraphArgs a) {
                 const int agent = r0 / TS;
                 float* xo = XB + (r0 + rg) * LDX;
                 if constexpr (MMA) {
-                    float macc[2][4][4];
-                    cfrag_fill(macc, nullptr, lane);
-                    mma_gemm_3xtf32<4>(macc, YB + r0 * LDX, gw + G_WS + l * XD * LDW, lane);
+                    float macc[MT][4][4];
+                    cfrag_fill<MT>(macc, nullptr, lane);
+                    mma_gemm_3xtf32<4, MT>(macc, YB + r0 * LDX, gw + G_WS + l * XD * LDW, lane);
                     const int g = lane >> 2, t = lane & 3;
 #pragma unroll
-                    for (int mt = 0; mt < 2; ++mt)
+                    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
                         for (int hh = 0; hh < 2; ++hh) {
                             const int rr = r0 + mt * 16 + g + 8 * hh;        // node row; s = its state inside the tile
@@ -712,13 +712,14 @@ static cudaError_t dispatch_tile(const GraphArgs& a, int num_sms, size_t max_sme
         if constexpr (N == 6) {
             // large batches: 32-row register tiles + 2 rows per thread in the per-state phases (least shared-memory
             // traffic per FFMA), two 6-warp CTAs per SM; up to one wave of tiles: 16-row tiles, 12 warps per CTA
-            // RGL_GRAPH_VARIANT (debug/experiments): '2' = 16-row FFMA tiles, '4' = 32-row FFMA tiles, 'm' = 32-row tiles with
-            // the shared-weight GEMMs on the tensor cores (mma.sync 3xTF32)
+            // default: shared-weight GEMMs on the tensor cores (mma.sync 3xTF32) unless the caller asks for fp32 FFMA or
+            // activation saves.  RGL_GRAPH_VARIANT (experiments): '2'/'4' = 16-/32-row FFMA tiles, 'n'/'m' = same with mma
             static const char* force = getenv("RGL_GRAPH_VARIANT");
-            const bool big = force ? (force[0] != '2') : (tiles32 > num_sms || (a.flags & RGL_FLAG_THROUGHPUT));
-            const bool mma = force ? (force[0] == 'm') : false;
-            if (big && mma && !a.save) return launch_graph<32, 4, 6, 2, true>(a, num_sms, max_smem, st);
+            const bool big = force ? (force[0] == '4' || force[0] == 'm') : (tiles32 > num_sms || (a.flags & RGL_FLAG_THROUGHPUT));
+            const bool mma = (force ? (force[0] == 'm' || force[0] == 'n') : true) && !a.save && !(a.flags & RGL_FLAG_FP32_FMA);
+            if (big && mma) return launch_graph<32, 4, 6, 2, true>(a, num_sms, max_smem, st);
             if (big) return launch_graph<32, 4, 6, 2>(a, num_sms, max_smem, st);
+            if (mma) return launch_graph<32, 2, 6, 0, true>(a, num_sms, max_smem, st);
         }
         return launch_graph<32, 2, N, 0>(a, num_sms, max_smem, st);
     }

@@ -49,6 +49,9 @@ class RGL(nn.Module):
         self._pack_cache = ops._PackCache()
         self._A_dev = None
         self._A_host = None
+        # numerics switch: large inference batches run their shared-weight GEMMs on the tensor cores with a 3xTF32 split
+        # (~3e-6 relative to fp32); set True to keep everything on the fp32 FMA pipe (~3e-7)
+        self.fp32_fma = False
 
     # ---- `.A`: attention matrix of the first sample, for visualisation (graph_model.py:116).  The
     # reference copies it to the host on every forward; here the copy happens when it is read.
@@ -69,7 +72,7 @@ class RGL(nn.Module):
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            if k in ('_pack_cache', '_A_dev', '_A_host'):
+            if k in ('_pack_cache', '_A_dev', '_A_host'):   # fp32_fma is a plain bool and is copied
                 continue
             setattr(new, k, copy.deepcopy(v, memo))
         new._pack_cache = ops._PackCache()
@@ -87,7 +90,8 @@ class RGL(nn.Module):
                 and self.human_state_dim == 5 and 1 <= self.num_layer <= _lib.MAX_LAYERS)
 
     def flags(self):
-        return (_lib.FLAG_SKIP if self.skip_connection else 0) | (_lib.FLAG_LAYERWISE if self.layerwise_graph else 0)
+        return ((_lib.FLAG_SKIP if self.skip_connection else 0) | (_lib.FLAG_LAYERWISE if self.layerwise_graph else 0)
+                | (_lib.FLAG_FP32_FMA if self.fp32_fma else 0))
 
     def param_tensors(self):
         return ops._graph_param_list(self)

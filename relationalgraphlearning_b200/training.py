@@ -69,7 +69,7 @@ def _graph_forward_train(g, robot, humans, extra_sizes, motion_blob=None, want_E
         cs.M[l], cs.Rl[l], cs.Hl[l] = sv['M'][l].data_ptr(), sv['Rl'][l].data_ptr(), sv['Hl'][l].data_ptr()
     cs.mh = sv['mh'].data_ptr() if want_S else None
     with torch.cuda.device(dev):
-        rc = _lib.lib().rgl_graph_forward_train(_lib.ptr(robot), _lib.ptr(humans), B, Nh, _lib.ptr(ops.packed_graph(g)), L, g.flags(),
+        rc = _lib.lib().rgl_graph_forward_train(_lib.ptr(robot), _lib.ptr(humans), B, Nh, _lib.ptr(ops.packed_graph(g)), L, g.flags() & ~_lib.FLAG_FP32_FMA,
                                                 _lib.ptr(motion_blob) if want_S else None, ctypes.byref(cs), None,
                                                 _lib.ptr(E), _lib.ptr(S), _lib.stream_ptr(dev))
     _lib.check(rc, 'rgl_graph_forward_train')

@@ -172,8 +172,16 @@ def test_full_size_properties_c2(cuda_device):
         perm = torch.randperm(B, device=cuda_device)
         assert torch.equal(ve((robot[perm], humans[perm])), V[perm])
         assert torch.equal(g1((robot[perm], humans[perm])), H[perm])
+        # chunks of 1000 states take the small-batch kernel (fp32 FFMA GEMMs), the full batch the tensor-core variant
+        # (3xTF32): equal within the parity tolerance, bit-identical when the same variant is forced
         parts = [ve((robot[i:i + 1000], humans[i:i + 1000])) for i in range(0, B, 1000)]
-        assert torch.equal(torch.cat(parts), V)
+        assert_close_scaled(torch.cat(parts), V, REL, 'V split')
+        g1.fp32_fma = True
+        Vf = ve((robot, humans))
+        parts = [ve((robot[i:i + 2048], humans[i:i + 2048])) for i in range(0, B, 2048)]
+        assert_close_scaled(torch.cat(parts), Vf, REL, 'V split fp32')
+        assert_close_scaled(Vf, V, REL, 'fp32 FFMA vs 3xTF32')
+        g1.fp32_fma = False
         # (2) the value head sees only the robot row: E from the H path equals the E-only path
         E = g1.run(robot, humans, want_E=True)['E']
         assert torch.equal(E, H[:, 0, :])
