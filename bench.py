@@ -501,10 +501,57 @@ def main():
     sampler.stop_flag = True
     sampler.join()
 
-    times = torch.tensor([t_ms, e2e_ms], dtype=torch.float64, device=dev)
+    # secondary numbers in the same run: the policy-facing call ValueEstimator.forward (graph forward + value head -> V),
+    # whose result is 16 KB per step instead of the 3.1 MB H tensor, device-resident and end to end
+    extra_ms = [0.0, 0.0]
+    if args.workload == 'graph':
+        K2 = min(K, 1000)
+        with torch.no_grad():
+            for i in range(W):
+                ve.run(robots_d[i % pool_n], humans_d[i % pool_n], throughput=args.streams > 1)
+        g2_ = torch.cuda.CUDAGraph()
+        keep2 = []
+        with torch.no_grad(), torch.cuda.stream(side):
+            with torch.cuda.graph(g2_, stream=side):
+                fork = torch.cuda.Event()
+                fork.record(side)
+                for b in branches:
+                    b.wait_event(fork)
+                for i in range(min(K2, 250)):
+                    with torch.cuda.stream(branches[i % nstreams]):
+                        keep2.append(ve.run(robots_d[i % pool_n], humans_d[i % pool_n], throughput=args.streams > 1))
+                for b in branches:
+                    ev = torch.cuda.Event()
+                    ev.record(b)
+                    side.wait_event(ev)
+        g2_.replay()
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(K2 // min(K2, 250)):
+            g2_.replay()
+        a1.record()
+        barrier()
+        K2 = (K2 // min(K2, 250)) * min(K2, 250)
+        extra_ms[0] = a0.elapsed_time(a1) / K2
+        hv = HostStream('value', ve, B, nh, dev, depth=depth)
+        for i in range(npin * depth):
+            hv.submit(robots_p[i % npin], humans_p[i % npin])
+        hv.drain()
+        barrier()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record(hv.streams[0])
+        for i in range(K2):
+            hv.submit(robots_p[i % npin], humans_p[i % npin])
+        hv.drain()
+        b1.record(hv.streams[0])
+        barrier()
+        extra_ms[1] = b0.elapsed_time(b1) / K2
+    times = torch.tensor([t_ms, e2e_ms] + extra_ms, dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     t_ms, e2e_ms = float(times[0]), float(times[1])
+    extra_ms = [float(times[2]), float(times[3])]
 
     if rank == 0:
         peaks = {}
@@ -534,6 +581,10 @@ def main():
                                       'note': 'binding roofline: %d FLOP/B >> fp32 ridge' % (aflops // abytes)}},
             'clocks': sampler.summary(),
         }
+        if extra_ms[0] > 0:
+            out['extra'] = {'value_path': {'call': 'ValueEstimator.forward = graph forward (E only) + value head -> V[B,1]',
+                                           'value': world * B / (extra_ms[0] * 1e-3), 'e2e': world * B / (extra_ms[1] * 1e-3),
+                                           'unit': 'states/s', 'd2h_bytes_per_step': B * 4}}
         if world == 1 and not args.no_cpu_baseline:
             rate, cores, sample, ms, k = cpu_reference_rate(args.workload, B, nh, min(K, 2000), 3, budget_s=15.0)
             out['cpu_baseline'] = {'value': rate, 'unit': 'states/s', 'cores': cores, 'kind': 'port', 'sample': sample,
