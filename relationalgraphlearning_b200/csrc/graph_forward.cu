@@ -703,27 +703,31 @@ static cudaError_t launch_graph(const GraphArgs& a, int num_sms, size_t max_smem
     return cudaGetLastError();
 }
 
+template <int TS, int RT, int N, int RPT>
+static cudaError_t launch_pick(const GraphArgs& a, bool mma, int num_sms, size_t max_smem, cudaStream_t st) {
+    return mma ? launch_graph<TS, RT, N, RPT, true>(a, num_sms, max_smem, st) : launch_graph<TS, RT, N, RPT, false>(a, num_sms, max_smem, st);
+}
+
 template <int N>
 static cudaError_t dispatch_tile(const GraphArgs& a, int num_sms, size_t max_smem, cudaStream_t st) {
+    // Numerics: inference runs the shared-weight GEMMs on the tensor cores (mma.sync, 3xTF32 split, ~3e-6 relative to
+    // fp32) unless the caller sets RGL_FLAG_FP32_FMA; the training forward (activation saves) always uses fp32 FFMA.
+    // RGL_GRAPH_VARIANT (experiments only): '2'/'4' = 16-/32-row FFMA tiles, 'n'/'m' = the same tiles with mma.
+    static const char* force = getenv("RGL_GRAPH_VARIANT");
+    const bool mma = (force ? (force[0] == 'm' || force[0] == 'n') : true) && !a.save && !(a.flags & RGL_FLAG_FP32_FMA);
     // pick the largest state tile that fits in shared memory; small batches prefer more CTAs
     const bool fits32 = graph_smem_bytes(32, a.Nh, a.L, a.mw != nullptr, N > 0) <= max_smem;
     const int tiles32 = (a.B + 31) / 32;
     if (fits32 && tiles32 >= num_sms / 2) {
         if constexpr (N == 6) {
-            // large batches: 32-row register tiles + 2 rows per thread in the per-state phases (least shared-memory
-            // traffic per FFMA), two 6-warp CTAs per SM; up to one wave of tiles: 16-row tiles, 12 warps per CTA
-            // default: shared-weight GEMMs on the tensor cores (mma.sync 3xTF32) unless the caller asks for fp32 FFMA or
-            // activation saves.  RGL_GRAPH_VARIANT (experiments): '2'/'4' = 16-/32-row FFMA tiles, 'n'/'m' = same with mma
-            static const char* force = getenv("RGL_GRAPH_VARIANT");
+            // beyond one wave of tiles (or multi-stream serving): 32-row tiles, 2 node rows per thread in the per-state
+            // phases, two 6-warp CTAs per SM; up to one wave: 16-row tiles, 12 warps per CTA (lowest latency)
             const bool big = force ? (force[0] == '4' || force[0] == 'm') : (tiles32 > num_sms || (a.flags & RGL_FLAG_THROUGHPUT));
-            const bool mma = (force ? (force[0] == 'm' || force[0] == 'n') : true) && !a.save && !(a.flags & RGL_FLAG_FP32_FMA);
-            if (big && mma) return launch_graph<32, 4, 6, 2, true>(a, num_sms, max_smem, st);
-            if (big) return launch_graph<32, 4, 6, 2>(a, num_sms, max_smem, st);
-            if (mma) return launch_graph<32, 2, 6, 0, true>(a, num_sms, max_smem, st);
+            if (big) return launch_pick<32, 4, 6, 2>(a, mma, num_sms, max_smem, st);
         }
-        return launch_graph<32, 2, N, 0>(a, num_sms, max_smem, st);
+        return launch_pick<32, 2, N, 0>(a, mma, num_sms, max_smem, st);
     }
-    if (graph_smem_bytes(16, a.Nh, a.L, a.mw != nullptr, N > 0) <= max_smem) return launch_graph<16, 2, N, 0>(a, num_sms, max_smem, st);
+    if (graph_smem_bytes(16, a.Nh, a.L, a.mw != nullptr, N > 0) <= max_smem) return launch_pick<16, 2, N, 0>(a, mma, num_sms, max_smem, st);
     return cudaErrorInvalidConfiguration;
 }
 
