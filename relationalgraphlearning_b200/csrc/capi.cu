@@ -2,8 +2,8 @@
 // queries, launches.  No torch types, no exceptions, no hidden synchronisation.
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include "kernels.h"
-
 
 namespace {
 thread_local char g_err[256] = "";
@@ -41,10 +41,10 @@ const char* rgl_last_error_string(void) { return g_err; }
 
 size_t rgl_packed_graph_floats(int num_layer) {
     if (num_layer < 1 || num_layer > RGL_MAX_LAYERS) return 0;
-    return (size_t)rgl::graph_floats(num_layer);
+    return (size_t)rgl::graph_floats_total(num_layer);
 }
 size_t rgl_packed_value_floats(void) { return rgl::VALUE_FLOATS; }
-size_t rgl_packed_motion_floats(void) { return rgl::MOTION_FLOATS; }
+size_t rgl_packed_motion_floats(void) { return rgl::MOTION_FLOATS_TOTAL; }
 
 int rgl_pack_graph(const RglGraphParams* p, float* packed, rgl_stream_t stream) {
     if (!p || !packed) return fail(RGL_EINVAL, "rgl_pack_graph: null argument");
@@ -91,7 +91,13 @@ int rgl_graph_forward(const float* robot, const float* humans, int B, int Nh, in
     a.H = H; a.E = E; a.S = S; a.A0 = A0; a.ntiles = 0; a.save = 0;
     memset(&a.sv, 0, sizeof(a.sv));
     a.use_tma = (humans_bcast == 1 && aligned16(robot) && aligned16(humans)) ? 1 : 0;
-    cudaError_t e = rgl::run_graph_forward(a, d.sms, d.max_smem, (cudaStream_t)stream);
+    // Inference runs on the tcgen05 kernel (3xTF32 products, fp32 accumulation in TMEM); RGL_FLAG_FP32_FMA keeps every
+    // product on the fp32 FMA pipe.  RGL_GRAPH_VARIANT (experiments only): 't' = tcgen05, anything else selects one of
+    // the legacy FFMA / mma.sync variants of graph_forward.cu.
+    static const char* variant = getenv("RGL_GRAPH_VARIANT");
+    const bool tc = (variant ? variant[0] == 't' : true) && !(flags & RGL_FLAG_FP32_FMA);
+    cudaError_t e = tc ? rgl::run_graph_forward_tc(a, d.sms, d.max_smem, (cudaStream_t)stream)
+                       : rgl::run_graph_forward(a, d.sms, d.max_smem, (cudaStream_t)stream);
     if (e == cudaErrorInvalidConfiguration) return fail(RGL_EUNSUPPORTED, "rgl_graph_forward: tile does not fit in shared memory");
     return e == cudaSuccess ? RGL_OK : fail_cuda(e, "rgl_graph_forward");
 }

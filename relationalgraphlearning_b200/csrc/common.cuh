@@ -52,6 +52,32 @@ constexpr int M_W1 = M_B0 + MH;                // [5][64]  (PyTorch layout: one 
 constexpr int M_B1 = M_W1 + HD * MH;           // [8] (5 used)
 constexpr int MOTION_FLOATS = M_B1 + 8;
 
+// ---- tensor-core (tcgen05) operand sections ------------------------------------------------------------
+// Appended to the packed graph / motion blobs (rgl_pack_* writes both the FMA and the tensor-core sections).
+// Every weight matrix is a B operand of tcgen05.mma kind::tf32: [n rows][32 k] K-major tiles in the UMMA
+// SWIZZLE_128B canonical layout (row = 128 B, 16-byte chunk c of row r stored at chunk c ^ (r & 7)), split into a
+// tf32 "hi" tile and a tf32 "lo" tile (w = hi + lo to ~2^-22) for the 3xTF32 product.  Offsets in floats.
+constexpr int T_W0   = 0;                       // emb layer 1, robot and human weights concatenated along k:
+                                                //   [64 hidden][k: 0-8 robot feats, 9-13 human feats, 14 robot bias, 15 human bias, 16-31 zero]
+                                                //   hi [64][32], lo at +2048
+constexpr int T_W1   = T_W0 + 4096;             // emb layer 2, stacked along n: rows 0-31 = w_h.2.weight, rows 32-63 = w_r.2.weight;
+                                                //   two k atoms: hi atoms at +0, +2048; lo atoms at +4096, +6144
+constexpr int T_WA   = T_W1 + 8192;             // layer-0 tile, stacked along n: rows 0-31 = w_a^T, rows 32-63 = Ws[0]^T (one N=64 MMA gives
+                                                //   Y = X w_a and X Ws[0] from a single A operand): hi [64][32], lo at +2048
+constexpr int T_WS1  = T_WA + 4096;             // layers l >= 1: Ws[l]^T hi [32][32] at T_WS1 + (l-1)*2048, lo at +1024
+__host__ __device__ constexpr int tc_bias_off(int L) { return T_WS1 + (L - 1) * 2048; }   // [0,32) = w_h.2.bias, [32,64) = w_r.2.bias
+__host__ __device__ constexpr int tc_graph_floats(int L) { return tc_bias_off(L) + 256; }
+__host__ __device__ constexpr int graph_tc_off(int L) { return (graph_floats(L) + 63) & ~63; }     // 256 B aligned
+__host__ __device__ constexpr int graph_floats_total(int L) { return graph_tc_off(L) + tc_graph_floats(L); }
+constexpr int TM_W0 = 0;                        // motion layer 1 (0.weight [64,32]): hi [64][32], lo at +2048
+constexpr int TM_B0 = 4096;                     // [64]
+constexpr int TM_W1 = TM_B0 + 64;               // 2.weight [5][64] (fp32, FMA pipe)
+constexpr int TM_B1 = TM_W1 + 320;              // [8] (5 used)
+constexpr int TMOTION_FLOATS = 4608;            // 18 KB
+constexpr int MOTION_TC_OFF = (MOTION_FLOATS + 63) & ~63;
+constexpr int MOTION_FLOATS_TOTAL = MOTION_TC_OFF + TMOTION_FLOATS;
+static_assert(TM_B1 + 8 <= TMOTION_FLOATS && tc_graph_floats(1) % 256 == 0, "tensor-core blob sections are 1 KB multiples");
+
 static_assert(graph_floats(2) - (2 * HID + 3 * XD) * (LDW - XD) == 8256, "graph parameter count (SURVEY.md 2b) + row padding");
 static_assert(graph_floats(RGL_MAX_LAYERS) % 4 == 0 && VALUE_FLOATS % 4 == 0 && MOTION_FLOATS % 4 == 0, "16B sections");
 

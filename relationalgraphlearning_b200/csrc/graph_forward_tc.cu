@@ -1,0 +1,540 @@
+// Fused RGL graph forward on the 5th-generation tensor cores (tcgen05 / TMEM) of sm_100a.
+//
+// Same contract as graph_forward.cu (crowd_nav/policy/graph_model.py:99-130 RGL.forward, :63-66 embedded_gaussian
+// similarity, crowd_nav/policy/state_predictor.py:28,36 motion head), different machine mapping:
+//
+//   group   = 128 threads = one UMMA M-tile of 128 graph-node rows = SPT = 128 / n whole states.  A thread owns ONE node
+//             row end to end (TMEM lane = row, tcgen05.ld/st 32x32b: thread t <-> lane t).  Groups are independent
+//             pipelines (own mbarrier, own named barrier, own 128 TMEM columns, own 16 KB feature buffer) that only
+//             share the weight tiles of their CTA: while one group waits for its MMAs the others compute.
+//   rows    = robot-first inside a tile: rows [0,SPT) are the robots of the SPT states, rows SPT + s*Nh + j the humans,
+//             so only the first warp holds robot rows (value path: the last layer runs for that warp only).
+//   GEMMs   = every shared-weight product (90% of the MACs) is tcgen05.mma kind::tf32, M=128, A operand in TMEM
+//             (written by the row-owning threads with tcgen05.st), B = weights resident in shared memory as UMMA
+//             SWIZZLE_128B K-major tiles, fp32 accumulation in TMEM.  fp32 accuracy comes from the 3xTF32 split
+//             x = hi + lo:  D += lo*Whi + hi*Wlo + hi*Whi  (measured 2.5e-7 relative on a K=32 dot, tools/umma_probe.cu;
+//             plain fp32 FMA chains give 2e-7).  A-in-TMEM matters: with A in shared memory an N=32 MMA is bound by
+//             the 4 KB operand fetch (85 cycles measured instead of 16).
+//             The robot / human embedding MLPs differ, so layer 1 concatenates them along k (robot features, human
+//             features and two indicator columns that carry the biases; a row has zeros in the other agent type's
+//             slots) and layer 2 stacks them along n (N=64: columns 0-31 human weights, 32-63 robot weights; each row
+//             keeps the half that belongs to it).
+//   per-state work (similarity row, softmax, A.H) stays on the FMA pipe, one node row per thread, neighbours' feature
+//             rows read from the group's swizzled shared-memory buffer; attention weights never leave registers.
+#include <stdlib.h>
+#include "kernels.h"
+
+namespace rgl {
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T, kind::tf32, issued by one thread for the whole CTA
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        :: "r"(d), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor, sm_100 version 1)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, tf32 x tf32, both K-major, M x N
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+#define RGL_R8(r, o)  "=r"(r[o]), "=r"(r[o + 1]), "=r"(r[o + 2]), "=r"(r[o + 3]), "=r"(r[o + 4]), "=r"(r[o + 5]), "=r"(r[o + 6]), "=r"(r[o + 7])
+#define RGL_I8(r, o)  "r"(r[o]), "r"(r[o + 1]), "r"(r[o + 2]), "r"(r[o + 3]), "r"(r[o + 4]), "r"(r[o + 5]), "r"(r[o + 6]), "r"(r[o + 7])
+// this thread's TMEM lane, 32 consecutive columns -> registers (load + wait in one asm block: results are defined after it)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : RGL_R8(r, 0), RGL_R8(r, 8), RGL_R8(r, 16), RGL_R8(r, 24)
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&r)[32], uint32_t (&q)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%64];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%65];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : RGL_R8(r, 0), RGL_R8(r, 8), RGL_R8(r, 16), RGL_R8(r, 24), RGL_R8(q, 0), RGL_R8(q, 8), RGL_R8(q, 16), RGL_R8(q, 24)
+        : "r"(taddr), "r"(taddr + 32) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 :: "r"(taddr), RGL_I8(r, 0), RGL_I8(r, 8) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// A-operand row: 16 / 32 values -> tf32 hi / lo columns of this thread's TMEM lane.  hi = x rounded to nearest tf32
+// (integer add of half an ulp, then mask: cvt.rna.tf32 is emulated with 3 instructions on sm_100), lo = x - hi exactly;
+// the tensor core drops the low 13 bits of lo (2^-23 relative to x).
+template <int NV>
+__device__ __forceinline__ void st_split(uint32_t t_hi, uint32_t t_lo, const float (&v)[NV]) {
+#pragma unroll
+    for (int b = 0; b < NV; b += 16) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            hi[j] = (__float_as_uint(v[b + j]) + 0x1000u) & 0xffffe000u;
+            lo[j] = __float_as_uint(v[b + j] - __uint_as_float(hi[j]));
+        }
+        tmem_st16(t_hi + b, hi);
+        tmem_st16(t_lo + b, lo);
+    }
+}
+
+// one elected thread: D[128 x N] (+)= A * W^T over KS k-steps of 8, 3xTF32 (small terms first).  Every operand is
+// warp-uniform (derived from __shfl_sync(.., 0) values), so each MMA is one UTCHMMA with uniform-register operands.
+template <int KS>
+__device__ __forceinline__ void issue_gemm(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t w_hi, uint32_t w_lo, uint32_t idesc, uint32_t acc) {
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+        const uint64_t bh = umma_desc(w_hi + ks * 32), bl = umma_desc(w_lo + ks * 32);
+        umma_tf32_ts(d, a_lo + ks * 8, bh, idesc, acc);
+        umma_tf32_ts(d, a_hi + ks * 8, bl, idesc, 1);
+        umma_tf32_ts(d, a_hi + ks * 8, bh, idesc, 1);
+        acc = 1;
+    }
+}
+
+// shared memory through 32-bit addresses (one LOP3 per swizzled access instead of 64-bit generic pointer arithmetic)
+__device__ __forceinline__ float4 lds128s(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void sts128s(uint32_t saddr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// [128][32] fp32 row buffer, swizzled like the UMMA SWIZZLE_128B tiles (chunk c of row r at chunk c ^ (r & 7)): row-per-thread
+// LDS/STS.128 are conflict-free.  row_ptr() = address of the row with its swizzle phase folded in; chunk c = row_ptr ^ (c << 4).
+__device__ __forceinline__ uint32_t row_ptr(uint32_t xf_s, int row) { return xf_s + row * 128 + ((row & 7) << 4); }
+__device__ __forceinline__ void xf_store_row(uint32_t rp, const float (&v)[32]) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) sts128s(rp ^ (c << 4), make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
+}
+
+// --------------------------------------------------------------------------------------------------- kernel
+constexpr int TC_COLS = 128;          // TMEM columns per group: [0,64) accumulators, [64,96) A hi, [96,128) A lo
+constexpr int C_D = 0, C_AHI = 64, C_ALO = 96;
+
+template <int N, int G>
+__global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tc_kernel(const GraphArgs a) {
+    constexpr int NMAX = N > 0 ? N : RGL_MAX_HUMANS + 1;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    float* smem = reinterpret_cast<float*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+
+    const int n = N > 0 ? N : a.Nh + 1;
+    const int Nh = n - 1;
+    const int SPT = 128 / n;                        // whole states per 128-row tile
+    const int twf = tc_graph_floats(a.L);
+    float* tw = smem;                               // graph operand tiles (1024 B aligned)
+    float* tm = tw + twf;                           // motion operand tiles (only when S is requested)
+    float* xf_all = tm + (a.mw ? TMOTION_FLOATS : 0);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xf_all + G * 4096);      // [0],[1] weights; [2+g] group g
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 2 + G);
+
+    const int tid = threadIdx.x, lane = tid & 31, gt = tid & 127;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // warp-uniform for the compiler
+    const int grp = warp >> 2, wq = warp & 3;
+    const bool skip = a.flags & RGL_FLAG_SKIP, layerwise = a.flags & RGL_FLAG_LAYERWISE;
+
+    if (warp == 0) tmem_alloc(tslot, TC_COLS * G);
+    if (tid == 0) {
+        for (int i = 0; i < 2 + G; ++i) mbar_init(bars + i, 1);
+        fence_mbar_init();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0) {
+        // stage 0: layer-1 embedding tiles (the first MMA needs only these); stage 1: everything else
+        const float* src = a.gw + graph_tc_off(a.L);
+        mbar_arrive_expect_tx(bars + 0, T_W1 * 4u);
+        bulk_g2s(tw, src, T_W1 * 4u, bars + 0);
+        const uint32_t rest = (uint32_t)(twf - T_W1) * 4u;
+        mbar_arrive_expect_tx(bars + 1, rest + (a.mw ? TMOTION_FLOATS * 4u : 0u));
+        bulk_g2s(tw + T_W1, src + T_W1, rest, bars + 1);
+        if (a.mw) bulk_g2s(tm, a.mw + MOTION_TC_OFF, TMOTION_FLOATS * 4u, bars + 1);
+    }
+
+    const uint32_t tbase = __shfl_sync(0xffffffffu, *tslot, 0);
+    const uint32_t tg = tbase + grp * TC_COLS;                        // this group's TMEM columns (lane field 0: MMA view)
+    const uint32_t tl = tg + ((uint32_t)(wq * 32) << 16);             // this warp's lane quadrant (ld / st view)
+    const uint32_t xf_s = __shfl_sync(0xffffffffu, smem_u32(xf_all), 0) + grp * 16384;
+    uint64_t* gbar = bars + 2 + grp;
+    uint32_t par = 0;
+    const uint32_t tw_s = __shfl_sync(0xffffffffu, smem_u32(tw), 0), tm_s = __shfl_sync(0xffffffffu, smem_u32(tm), 0);   // warp-uniform for the compiler
+    const bool issuer = wq == 0;                                      // warp-uniform; lane 0 of that warp issues the MMAs
+    auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" :: "r"(grp + 1) : "memory"); };
+    auto mma_wait = [&]() { mbar_wait(gbar, par); par ^= 1; tc_fence_after(); };
+    // A operand written -> visible to the MMAs issued after the barrier
+    auto publish = [&]() { tmem_st_wait(); tc_fence_before(); group_sync(); };
+
+    // row identity inside a tile (the same for every tile)
+    const bool is_robot = gt < SPT;
+    const int hrow = gt - SPT;
+    const int s_loc = is_robot ? gt : hrow / Nh;                      // state inside the tile
+    const int hum = is_robot ? 0 : hrow - s_loc * Nh;                 // human index
+    const bool row_used = gt < SPT * n;
+    const int node = is_robot ? 0 : hum + 1;
+    const int hbase = SPT + s_loc * Nh;                               // first human row of this thread's state
+    const uint32_t my_row = row_ptr(xf_s, gt);
+    const bool robot_warps = wq * 32 < SPT;                           // warp-uniform: this warp holds at least one robot row
+
+    const int ntiles = a.ntiles;
+    const int tstride = gridDim.x * G;
+    float xr[RD];
+    auto load_raw = [&](int tile) {
+        const long gs = (long)tile * SPT + s_loc;
+#pragma unroll
+        for (int k = 0; k < RD; ++k) xr[k] = 0.f;
+        if (tile < ntiles && row_used && gs < a.B) {
+            if (is_robot) {
+                const float* p = a.robot + gs * RD;
+#pragma unroll
+                for (int k = 0; k < RD; ++k) xr[k] = __ldg(p + k);
+            } else {
+                const float* p = a.humans + ((gs / a.hb) * Nh + hum) * HD;
+#pragma unroll
+                for (int k = 0; k < HD; ++k) xr[k] = __ldg(p + k);
+            }
+        }
+    };
+    int tile = blockIdx.x * G + grp;
+    load_raw(tile);
+    bool first = true;
+
+    for (; tile < ntiles; tile += tstride) {
+        const long s0 = (long)tile * SPT;
+        const int cnt = (int)min((long)SPT, (long)a.B - s0);
+        const bool valid = row_used && s_loc < cnt;
+
+        // ================= embedding layer 1: hidden = relu([x_r | x_h | 1_r | 1_h] . W0cat^T), K = 16, N = 64 =================
+        {
+            float a0[16];
+#pragma unroll
+            for (int k = 0; k < RD; ++k) a0[k] = is_robot ? xr[k] : 0.f;
+#pragma unroll
+            for (int k = 0; k < HD; ++k) a0[RD + k] = is_robot ? 0.f : xr[k];
+            a0[14] = (valid && is_robot) ? 1.f : 0.f;
+            a0[15] = (valid && !is_robot) ? 1.f : 0.f;
+            st_split<16>(tl + C_AHI, tl + C_ALO, a0);
+        }
+        publish();
+        if (issuer) {
+            if (lane == 0) {
+                if (first) mbar_wait(bars + 0, 0);
+                tc_fence_after();
+                issue_gemm<2>(tg + C_D, tg + C_AHI, tg + C_ALO, tw_s + T_W0 * 4, tw_s + (T_W0 + 2048) * 4, umma_idesc(128, 64), 0);
+                umma_commit(gbar);
+            }
+            __syncwarp();
+        }
+        load_raw(tile + tstride);            // next tile's raw state: in flight under this tile's phases
+        mma_wait();
+
+        // ================= embedding layer 2: [X_h | X_r] = hidden . [W1_h ; W1_r]^T, K = 64 in two halves, N = 64 =================
+        float x[32];
+        {
+            uint32_t h0[32], h1[32];
+            tmem_ld64(tl + C_D, h0, h1);     // the whole hidden row leaves TMEM before the accumulator columns are reused
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(__uint_as_float(h0[j]), 0.f);
+            st_split<32>(tl + C_AHI, tl + C_ALO, v);
+            publish();
+            if (issuer) {
+                if (lane == 0) {
+                    if (first) mbar_wait(bars + 1, 0);
+                    tc_fence_after();
+                    issue_gemm<4>(tg + C_D, tg + C_AHI, tg + C_ALO, tw_s + T_W1 * 4, tw_s + (T_W1 + 4096) * 4, umma_idesc(128, 64), 0);
+                    umma_commit(gbar);
+                }
+                __syncwarp();
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(__uint_as_float(h1[j]), 0.f);
+            mma_wait();                      // first half consumed: its A columns may be overwritten
+            st_split<32>(tl + C_AHI, tl + C_ALO, v);
+            publish();
+            if (issuer) {
+                if (lane == 0) {
+                    tc_fence_after();
+                    issue_gemm<4>(tg + C_D, tg + C_AHI, tg + C_ALO, tw_s + (T_W1 + 2048) * 4, tw_s + (T_W1 + 4096 + 2048) * 4, umma_idesc(128, 64), 1);
+                    umma_commit(gbar);
+                }
+                __syncwarp();
+            }
+            if (first) { mbar_wait(bars + 1, 0); first = false; }      // the biases arrive with stage 1
+            mma_wait();
+            tmem_ld64(tl + C_D, h0, h1);     // h0 = human-weight version, h1 = robot-weight version
+            const float* bias = tw + tc_bias_off(a.L) + (is_robot ? 32 : 0);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float4 b = lds128(bias + 4 * c);
+                x[4 * c + 0] = fmaxf(__uint_as_float(is_robot ? h1[4 * c + 0] : h0[4 * c + 0]) + b.x, 0.f);
+                x[4 * c + 1] = fmaxf(__uint_as_float(is_robot ? h1[4 * c + 1] : h0[4 * c + 1]) + b.y, 0.f);
+                x[4 * c + 2] = fmaxf(__uint_as_float(is_robot ? h1[4 * c + 2] : h0[4 * c + 2]) + b.z, 0.f);
+                x[4 * c + 3] = fmaxf(__uint_as_float(is_robot ? h1[4 * c + 3] : h0[4 * c + 3]) + b.w, 0.f);
+            }
+        }
+        xf_store_row(my_row, x);             // feature rows for the neighbours' similarity logits
+
+        // ================= GCN layers: H' = relu(A (H W_l)) (+ H) =================
+        // (the reference evaluates (A H) W_l; the products are reassociated so that H W_l shares its A operand with Y = H w_a)
+        float p[NMAX];
+        for (int l = 0; l < a.L; ++l) {
+            const bool last = (l == a.L - 1);
+            const bool robot_only = last && a.H == nullptr && a.S == nullptr;
+            const bool active = !robot_only || robot_warps;          // warp-uniform
+            const bool sim = (l == 0) || layerwise;
+
+            st_split<32>(tl + C_AHI, tl + C_ALO, x);
+            publish();       // also: feature rows in xf visible; every read of the previous layer's H W rows is done
+            if (issuer) {
+                if (lane == 0) {
+                    tc_fence_after();
+                    if (l == 0) {
+                        // one N = 64 MMA chain: columns [0,32) = Y = X w_a, columns [32,64) = X Ws[0]
+                        issue_gemm<4>(tg + C_D, tg + C_AHI, tg + C_ALO, tw_s + T_WA * 4, tw_s + (T_WA + 2048) * 4, umma_idesc(128, 64), 0);
+                    } else {
+                        if (layerwise)
+                            issue_gemm<4>(tg + C_D, tg + C_AHI, tg + C_ALO, tw_s + T_WA * 4, tw_s + (T_WA + 2048) * 4, umma_idesc(128, 32), 0);
+                        const uint32_t ws = tw_s + (T_WS1 + (l - 1) * 2048) * 4;
+                        issue_gemm<4>(tg + C_D + 32, tg + C_AHI, tg + C_ALO, ws, ws + 4096, umma_idesc(128, 32), 0);
+                    }
+                    umma_commit(gbar);
+                }
+                __syncwarp();
+            }
+            mma_wait();
+
+            if (sim) {
+                // ---- this row's similarity logits against the state's feature rows + softmax (FMA pipe) ----
+                if (active) {                                // warp-uniform: tcgen05.ld is warp-collective
+                    uint32_t yr[32];
+                    tmem_ld32(tl + C_D, yr);
+                    if (row_used) {
+                    float mx = -INFINITY;
+#pragma unroll
+                    for (int j = 0; j < NMAX; ++j) {
+                        if (N > 0 || j < n) {
+                            const uint32_t rp = row_ptr(xf_s, j == 0 ? s_loc : hbase + j - 1);
+                            float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) {
+                                const float4 xv = lds128s(rp ^ (c << 4));
+                                d0 = fmaf(__uint_as_float(yr[4 * c + 0]), xv.x, d0);
+                                d1 = fmaf(__uint_as_float(yr[4 * c + 1]), xv.y, d1);
+                                d2 = fmaf(__uint_as_float(yr[4 * c + 2]), xv.z, d2);
+                                d3 = fmaf(__uint_as_float(yr[4 * c + 3]), xv.w, d3);
+                            }
+                            p[j] = (d0 + d1) + (d2 + d3);
+                            mx = fmaxf(mx, p[j]);
+                        }
+                    }
+                    float sum = 0.f;
+#pragma unroll
+                    for (int j = 0; j < NMAX; ++j)
+                        if (N > 0 || j < n) { p[j] = expf(p[j] - mx); sum += p[j]; }
+#pragma unroll
+                    for (int j = 0; j < NMAX; ++j)
+                        if (N > 0 || j < n) p[j] = p[j] / sum;
+                    if (a.A0 != nullptr && l == 0 && tile == 0 && s_loc == 0) {
+#pragma unroll
+                        for (int j = 0; j < NMAX; ++j)
+                            if (N > 0 || j < n) a.A0[node * n + j] = p[j];
+                    }
+                    }
+                }
+                group_sync();                                // every read of the feature rows is done
+            }
+
+            // ---- H W rows -> xf; H' = relu(sum_j A[i][j] (H W)[j]) (+ H) ----
+            {
+                uint32_t hw[32];
+                tmem_ld32(tl + C_D + 32, hw);
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    sts128s(my_row ^ (c << 4), make_float4(__uint_as_float(hw[4 * c]), __uint_as_float(hw[4 * c + 1]),
+                                                           __uint_as_float(hw[4 * c + 2]), __uint_as_float(hw[4 * c + 3])));
+            }
+            tc_fence_before();
+            group_sync();
+            if (active && row_used) {
+                float acc[32];
+#pragma unroll
+                for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+#pragma unroll
+                for (int j = 0; j < NMAX; ++j) {
+                    if (N > 0 || j < n) {
+                        const uint32_t rp = row_ptr(xf_s, j == 0 ? s_loc : hbase + j - 1);
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const float4 hv = lds128s(rp ^ (c << 4));
+                            acc[4 * c + 0] = fmaf(p[j], hv.x, acc[4 * c + 0]);
+                            acc[4 * c + 1] = fmaf(p[j], hv.y, acc[4 * c + 1]);
+                            acc[4 * c + 2] = fmaf(p[j], hv.z, acc[4 * c + 2]);
+                            acc[4 * c + 3] = fmaf(p[j], hv.w, acc[4 * c + 3]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const float v = fmaxf(acc[c], 0.f);
+                    x[c] = skip ? v + x[c] : v;
+                }
+            }
+            if (!last && layerwise) {                        // the next layer's similarity needs the new feature rows
+                group_sync();
+                xf_store_row(my_row, x);
+            }
+        }
+
+        // ================= outputs =================
+        if (a.E != nullptr && is_robot && valid) {
+            float* e = a.E + (s0 + s_loc) * XD;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) *reinterpret_cast<float4*>(e + 4 * c) = make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+        }
+        if (a.S != nullptr) {
+            // state-predictor head on every row (robot rows are computed and dropped): relu(H W0^T + b0) on the tensor
+            // cores (N = 64), the 64 -> 5 output layer per thread on the FMA pipe
+            st_split<32>(tl + C_AHI, tl + C_ALO, x);
+            publish();
+            if (issuer) {
+                if (lane == 0) {
+                    tc_fence_after();
+                    issue_gemm<4>(tg + C_D, tg + C_AHI, tg + C_ALO, tm_s + TM_W0 * 4, tm_s + (TM_W0 + 2048) * 4, umma_idesc(128, 64), 0);
+                    umma_commit(gbar);
+                }
+                __syncwarp();
+            }
+            mma_wait();
+            uint32_t h0[32], h1[32];
+            tmem_ld64(tl + C_D, h0, h1);
+            float part[HD];
+#pragma unroll
+            for (int c = 0; c < HD; ++c) part[c] = tm[TM_B1 + c];
+#pragma unroll
+            for (int k4 = 0; k4 < 16; ++k4) {
+                const float4 b = lds128(tm + TM_B0 + 4 * k4);
+                const uint32_t* hh = k4 < 8 ? h0 : h1;
+                const int o = (k4 & 7) * 4;
+                const float v0 = fmaxf(__uint_as_float(hh[o + 0]) + b.x, 0.f), v1 = fmaxf(__uint_as_float(hh[o + 1]) + b.y, 0.f);
+                const float v2 = fmaxf(__uint_as_float(hh[o + 2]) + b.z, 0.f), v3 = fmaxf(__uint_as_float(hh[o + 3]) + b.w, 0.f);
+#pragma unroll
+                for (int c = 0; c < HD; ++c) {
+                    const float4 w = lds128(tm + TM_W1 + c * MH + 4 * k4);
+                    part[c] = fmaf(v0, w.x, part[c]); part[c] = fmaf(v1, w.y, part[c]);
+                    part[c] = fmaf(v2, w.z, part[c]); part[c] = fmaf(v3, w.w, part[c]);
+                }
+            }
+            if (!is_robot && valid) {
+                float* so = a.S + ((s0 + s_loc) * Nh + hum) * HD;
+#pragma unroll
+                for (int c = 0; c < HD; ++c) so[c] = part[c];
+            }
+        }
+        if (a.H != nullptr) {
+            // stage the final rows in xf, then copy out in HBM order: 512 contiguous bytes per warp instruction
+            group_sync();                                    // every read of the last H W rows is done
+            xf_store_row(my_row, x);
+            group_sync();
+            float* dst = a.H + s0 * n * XD;
+            const int chunks = cnt * n * 8;
+            for (int idx = gt; idx < chunks; idx += 128) {
+                const int orow = idx >> 3, c = idx & 7;
+                const int s = orow / n, i = orow - s * n;
+                const int srow = i == 0 ? s : SPT + s * Nh + i - 1;
+                *reinterpret_cast<float4*>(dst + (size_t)idx * 4) = lds128s(row_ptr(xf_s, srow) ^ (c << 4));
+            }
+            // the next tile writes xf only after further group barriers: no extra barrier needed here
+        }
+    }
+
+    // teardown: the bulk copies must have landed before the CTA's shared memory is released
+    if (tid == 0) { mbar_wait(bars + 0, 0); mbar_wait(bars + 1, 0); }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, TC_COLS * G);
+}
+
+// ---------------------------------------------------------------------------------------------------
+static size_t tc_smem_bytes(int L, bool motion, int G) {
+    return 1024 + ((size_t)tc_graph_floats(L) + (motion ? TMOTION_FLOATS : 0) + (size_t)G * 4096) * 4 + (2 + G) * 8 + 16;
+}
+
+template <int N, int G>
+static cudaError_t launch_tc(const GraphArgs& a, int num_sms, size_t max_smem, cudaStream_t st) {
+    const int n = a.Nh + 1;
+    const size_t smem = tc_smem_bytes(a.L, a.mw != nullptr, G);
+    if (smem > max_smem) return cudaErrorInvalidConfiguration;
+    GraphArgs b = a;
+    const int spt = 128 / n;
+    b.ntiles = (a.B + spt - 1) / spt;
+    static bool attr_set = false;     // benign race: idempotent
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(graph_forward_tc_kernel<N, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    int per_sm = (int)((228 * 1024) / (smem + 1024));
+    const int max_cta = G <= 2 ? 2 : 1;                       // matches __launch_bounds__ and the 512 TMEM columns of an SM
+    if (per_sm > max_cta) per_sm = max_cta;
+    if (per_sm < 1) per_sm = 1;
+    const int want = (b.ntiles + G - 1) / G;
+    const int grid = want < num_sms * per_sm ? want : num_sms * per_sm;
+    graph_forward_tc_kernel<N, G><<<grid, 128 * G, smem, st>>>(b);
+    return cudaGetLastError();
+}
+
+template <int N>
+static cudaError_t dispatch_tc(const GraphArgs& a, int num_sms, size_t max_smem, cudaStream_t st) {
+    // RGL_TC_GROUPS (experiments only): force the number of 128-row groups per CTA
+    static const char* force = getenv("RGL_TC_GROUPS");
+    const int n = a.Nh + 1, spt = 128 / n;
+    const int ntiles = (a.B + spt - 1) / spt;
+    int g = force ? atoi(force) : 0;
+    if (g != 1 && g != 2 && g != 4) {
+        // the state-predictor tiles do not leave room for two CTAs per SM: one CTA of four groups shares one weight copy.
+        // Small batches (at most two tiles per SM): one group per CTA so that the tiles spread over all SMs.
+        g = a.mw != nullptr ? 4 : (ntiles <= 2 * num_sms ? 1 : 2);
+    }
+    if (g == 1) return launch_tc<N, 1>(a, num_sms, max_smem, st);
+    if (g == 2) return launch_tc<N, 2>(a, num_sms, max_smem, st);
+    return launch_tc<N, 4>(a, num_sms, max_smem, st);
+}
+
+cudaError_t run_graph_forward_tc(const GraphArgs& a, int num_sms, size_t max_smem, cudaStream_t st) {
+    switch (a.Nh + 1) {
+        case 6: return dispatch_tc<6>(a, num_sms, max_smem, st);
+        case 11: return dispatch_tc<11>(a, num_sms, max_smem, st);
+        case 21: return dispatch_tc<21>(a, num_sms, max_smem, st);
+        default: return dispatch_tc<0>(a, num_sms, max_smem, st);
+    }
+}
+
+}  // namespace rgl

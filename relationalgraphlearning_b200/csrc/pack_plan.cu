@@ -23,8 +23,44 @@ __device__ __forceinline__ void pack_rows(float* dst, const float* src, int K, i
     }
 }
 
+// ---- tensor-core operand tiles (common.cuh "tensor-core operand sections") ----------------------------------
+__device__ __forceinline__ float rna_tf32f(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+// element (row, k) of a [rows][32] K-major SWIZZLE_128B tile; hi tile at `tile`, lo tile at `tile + lo_off`
+__device__ __forceinline__ void tc_put(float* tile, int lo_off, int row, int k, float w) {
+    const int idx = row * 32 + ((((k >> 2) ^ row) & 7) << 2) + (k & 3);
+    const float hi = rna_tf32f(w);
+    tile[idx] = hi;
+    tile[lo_off + idx] = rna_tf32f(w - hi);
+}
+
+__device__ void pack_graph_tc(const RglGraphParams& p, float* tc, int t, int nt) {
+    for (int idx = t; idx < HID * 32; idx += nt) {          // emb layer 1: k-concatenated robot | human | biases
+        const int u = idx >> 5, k = idx & 31;
+        const float w = k < RD ? p.wr0_w[u * RD + k] : k < RD + HD ? p.wh0_w[u * HD + (k - RD)] : k == 14 ? p.wr0_b[u] : k == 15 ? p.wh0_b[u] : 0.f;
+        tc_put(tc + T_W0, 2048, u, k, w);
+    }
+    for (int idx = t; idx < 64 * HID; idx += nt) {          // emb layer 2: n-stacked human (rows 0-31) | robot (rows 32-63)
+        const int row = idx / HID, k = idx - row * HID;
+        const float w = row < XD ? p.wh1_w[row * HID + k] : p.wr1_w[(row - XD) * HID + k];
+        tc_put(tc + T_W1 + (k >> 5) * 2048, 4096, row, k & 31, w);
+    }
+    for (int idx = t; idx < XD * XD; idx += nt) {           // X @ W uses W[k][n]: B operand row n holds column n
+        const int nn = idx >> 5, k = idx & 31;
+        tc_put(tc + T_WA, 2048, nn, k, p.w_a[k * XD + nn]);
+        tc_put(tc + T_WA, 2048, XD + nn, k, p.Ws[0][k * XD + nn]);
+        for (int l = 1; l < p.num_layer; ++l) tc_put(tc + T_WS1 + (l - 1) * 2048, 1024, nn, k, p.Ws[l][k * XD + nn]);
+    }
+    float* b = tc + tc_bias_off(p.num_layer);
+    for (int idx = t; idx < 256; idx += nt) b[idx] = idx < XD ? p.wh1_b[idx] : idx < 2 * XD ? p.wr1_b[idx - XD] : 0.f;
+}
+
 __global__ void pack_graph_kernel(RglGraphParams p, float* out) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    pack_graph_tc(p, out + graph_tc_off(p.num_layer), t, nt);
     pack_linear_T(out + G_WR0, p.wr0_w, HID, RD, HID, t, nt);
     pack_copy(out + G_BR0, p.wr0_b, HID, HID, t, nt);
     pack_linear_T(out + G_WR1, p.wr1_w, XD, HID, LDW, t, nt);
@@ -55,6 +91,11 @@ __global__ void pack_motion_kernel(RglMotionParams p, float* out) {
     pack_copy(out + M_B0, p.b0, MH, MH, t, nt);
     pack_copy(out + M_W1, p.w1, HD * MH, HD * MH, t, nt);
     pack_copy(out + M_B1, p.b1, HD, 8, t, nt);
+    float* tc = out + MOTION_TC_OFF;
+    for (int idx = t; idx < MH * XD; idx += nt) tc_put(tc + TM_W0, 2048, idx >> 5, idx & 31, p.w0[idx]);
+    pack_copy(tc + TM_B0, p.b0, MH, MH, t, nt);
+    pack_copy(tc + TM_W1, p.w1, HD * MH, HD * MH, t, nt);
+    pack_copy(tc + TM_B1, p.b1, HD, 8, t, nt);
 }
 
 // ---- planner: one thread per (state e, action a) ------------------------------------------------------

@@ -1,0 +1,398 @@
+// tcgen05 (UMMA) probe for sm_100a: validates the shared-memory / instruction descriptors, the TMEM load pattern and
+// the 3xTF32 split used by relationalgraphlearning_b200/csrc/graph_forward_tc.cu, and measures the latency of one
+// "phase" (STS operands -> fence -> barrier -> MMAs -> commit -> mbarrier wait -> tcgen05.ld).
+//
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/umma_probe tools/umma_probe.cu
+//   tools/umma_probe <test>      test = 1 (1xTF32 SS, K=32,N=32)  2 (3xTF32 SS)  3 (3xTF32 SS, K=64, N=64)
+//                                       4 (3xTF32, A from TMEM)    5 (phase latency, 1 and 2 groups)
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(2); } } while (0)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, kind::tf32
+__device__ __forceinline__ void umma_tf32_ss(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+// A from TMEM
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        :: "r"(d), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t rna_tf32(float x) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = rna_tf32(x);
+    lo = rna_tf32(x - __uint_as_float(hi));
+}
+
+// K-major SWIZZLE_128B operand tile: rows of 128 B (32 tf32), 8-row groups of 1024 B, 16-byte chunk c of row r stored at
+// chunk (c ^ (r & 7)).  Tile base must be 1024-byte aligned.
+__device__ __forceinline__ uint32_t sw128(int r, int c) { return (uint32_t)r * 128u + (uint32_t)(((c ^ r) & 7) << 4); }
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);     // start address >> 4, bits [0,14)
+    d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset: 8 rows x 128 B
+    d |= (uint64_t)1 << 46;                        // descriptor version 1 (sm_100)
+    d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+    return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// D[128][N] = X[128][K] * W[K][N];   MODE 0: single TF32 (operands as they are), 1: 3xTF32 SS, 2: 3xTF32 with A in TMEM
+template <int K, int N, int MODE>
+__global__ void __launch_bounds__(128) gemm_probe(const float* __restrict__ X, const float* __restrict__ W, float* __restrict__ D) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int KA = K / 32;                      // 32-wide K atoms
+    uint8_t* Ahi = smem;                            // KA x [128][32]
+    uint8_t* Alo = Ahi + KA * 16384;
+    uint8_t* Bhi = Alo + KA * 16384;                // KA x [N][32]   (B[n][k] = W[k][n])
+    uint8_t* Blo = Bhi + KA * N * 128;
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tslot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    constexpr uint32_t TCOLS = 256;
+    if (warp == 0) tmem_alloc(&tslot, TCOLS);
+    if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = tslot;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+
+    // A operand: thread = row
+    for (int ka = 0; ka < KA; ++ka)
+        for (int c = 0; c < 8; ++c) {
+            const float4 v = *reinterpret_cast<const float4*>(X + tid * K + ka * 32 + c * 4);
+            uint32_t h[4], l[4];
+            if (MODE == 0) { h[0] = __float_as_uint(v.x); h[1] = __float_as_uint(v.y); h[2] = __float_as_uint(v.z); h[3] = __float_as_uint(v.w); l[0] = l[1] = l[2] = l[3] = 0; }
+            else { split_tf32(v.x, h[0], l[0]); split_tf32(v.y, h[1], l[1]); split_tf32(v.z, h[2], l[2]); split_tf32(v.w, h[3], l[3]); }
+            *reinterpret_cast<uint4*>(Ahi + ka * 16384 + sw128(tid, c)) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(Alo + ka * 16384 + sw128(tid, c)) = make_uint4(l[0], l[1], l[2], l[3]);
+        }
+    if (MODE == 2) {     // A in TMEM: lane = row, column = k; hi at columns [64, 64+K), lo at [128, 128+K)
+        for (int k8 = 0; k8 < K / 8; ++k8) {
+            uint32_t h[8], l[8];
+            for (int j = 0; j < 8; ++j) split_tf32(X[tid * K + k8 * 8 + j], h[j], l[j]);
+            tmem_st8(tbase + lane_base + 64 + k8 * 8, h);
+            tmem_st8(tbase + lane_base + 128 + k8 * 8, l);
+        }
+        tmem_st_wait();
+    }
+    // B operand: row n of atom ka holds W[ka*32 .. ka*32+31][n]
+    for (int idx = tid; idx < KA * N * 8; idx += 128) {
+        const int c = idx & 7, n = (idx >> 3) % N, ka = idx / (8 * N);
+        uint32_t h[4], l[4];
+        for (int j = 0; j < 4; ++j) {
+            const float w = W[(ka * 32 + c * 4 + j) * N + n];
+            if (MODE == 0) { h[j] = __float_as_uint(w); l[j] = 0; } else split_tf32(w, h[j], l[j]);
+        }
+        *reinterpret_cast<uint4*>(Bhi + ka * N * 128 + sw128(n, c)) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(Blo + ka * N * 128 + sw128(n, c)) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+        tc_fence_after();
+        constexpr uint32_t idesc = make_idesc(128, N);
+        uint32_t acc = 0;
+        for (int ka = 0; ka < KA; ++ka)
+            for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t ah = make_desc(smem_u32(Ahi + ka * 16384) + ks * 32), al = make_desc(smem_u32(Alo + ka * 16384) + ks * 32);
+                const uint64_t bh = make_desc(smem_u32(Bhi + ka * N * 128) + ks * 32), bl = make_desc(smem_u32(Blo + ka * N * 128) + ks * 32);
+                const uint32_t kcol = ka * 32 + ks * 8;
+                if (MODE == 0) {
+                    umma_tf32_ss(tbase, ah, bh, idesc, acc); acc = 1;
+                } else if (MODE == 1) {
+                    umma_tf32_ss(tbase, al, bh, idesc, acc); acc = 1;      // small terms first
+                    umma_tf32_ss(tbase, ah, bl, idesc, 1);
+                    umma_tf32_ss(tbase, ah, bh, idesc, 1);
+                } else {
+                    umma_tf32_ts(tbase, tbase + 128 + kcol, bh, idesc, acc); acc = 1;
+                    umma_tf32_ts(tbase, tbase + 64 + kcol, bl, idesc, 1);
+                    umma_tf32_ts(tbase, tbase + 64 + kcol, bh, idesc, 1);
+                }
+            }
+        umma_commit(&bar);
+    }
+    mbar_wait(&bar, 0);
+    tc_fence_after();
+    for (int n0 = 0; n0 < N; n0 += 32) {
+        float v[32];
+        tmem_ld32(tbase + lane_base + n0, v);
+        for (int j = 0; j < 32; ++j) D[tid * N + n0 + j] = v[j];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, TCOLS);
+}
+
+template <int K, int N, int MODE>
+static int run_gemm(const char* name) {
+    std::vector<float> X(128 * K), W(K * N), D(128 * N);
+    srand(1234);
+    for (auto& v : X) v = (float)rand() / RAND_MAX * 20.f - 4.f;
+    for (auto& v : W) v = (float)rand() / RAND_MAX * 2.f - 1.f;
+    float *dX, *dW, *dD;
+    CK(cudaMalloc(&dX, X.size() * 4)); CK(cudaMalloc(&dW, W.size() * 4)); CK(cudaMalloc(&dD, D.size() * 4));
+    CK(cudaMemcpy(dX, X.data(), X.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dW, W.data(), W.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemset(dD, 0xff, D.size() * 4));
+    const size_t smem = 1024 + 2 * (K / 32) * 16384 + 2 * (K / 32) * N * 128;
+    CK(cudaFuncSetAttribute(gemm_probe<K, N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gemm_probe<K, N, MODE><<<1, 128, smem>>>(dX, dW, dD);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+    double max_err = 0, max_err32 = 0, scale = 0;
+    for (int r = 0; r < 128; ++r)
+        for (int n = 0; n < N; ++n) {
+            double ref = 0; float ref32 = 0.f;
+            for (int k = 0; k < K; ++k) {
+                float x = X[r * K + k], w = W[k * N + n];
+                if (MODE == 0) {     // hardware truncation or rounding? compare against both below; here: exact operands
+                }
+                ref += (double)x * (double)w;
+                ref32 = fmaf(x, w, ref32);
+            }
+            max_err = fmax(max_err, fabs(D[r * N + n] - ref));
+            max_err32 = fmax(max_err32, fabs((double)ref32 - ref));
+            scale = fmax(scale, fabs(ref));
+        }
+    printf("%s: K=%d N=%d  max|D-ref64| = %.3e (rel %.3e)   fp32-FMA err %.3e   D[0][0..3] = %g %g %g %g  D[127][N-1] = %g\n", name, K, N, max_err,
+           max_err / scale, max_err32, D[0], D[1], D[2], D[3], D[127 * N + N - 1]);
+    const double tol = MODE == 0 ? 2e-3 : 2e-6;
+    const bool ok = max_err / scale < tol;
+    printf("%s: %s\n", name, ok ? "PASS" : "FAIL");
+    return ok ? 0 : 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// phase latency: G groups of 128 threads; each iteration: every thread writes its row (hi+lo, 16 STS.128), fence, group
+// barrier, one thread issues 12 MMAs (K=32, N=32, 3xTF32) + commit, all wait, tcgen05.ld 32 columns.
+template <int G>
+__global__ void __launch_bounds__(128 * G) phase_probe(float* out, long long* cycles, int iters) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t bar[G];
+    __shared__ uint32_t tslot;
+    const int tid = threadIdx.x, warp = tid >> 5, grp = tid >> 7, gt = tid & 127;
+    uint8_t* Ahi = smem + grp * 32768;
+    uint8_t* Alo = Ahi + 16384;
+    uint8_t* Bhi = smem + G * 32768;
+    uint8_t* Blo = Bhi + 4096;
+    if (warp == 0) tmem_alloc(&tslot, 64 * G >= 32 ? 64 * G : 32);
+    if (tid == 0) { for (int g = 0; g < G; ++g) mbar_init(&bar[g], 1); fence_mbar_init(); }
+    for (int idx = tid; idx < 2048; idx += blockDim.x) reinterpret_cast<uint32_t*>(Bhi)[idx] = idx < 1024 ? rna_tf32(0.001f * (idx % 97)) : 0u;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = tslot + grp * 64;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    float v[32];
+    for (int j = 0; j < 32; ++j) v[j] = 0.01f * (gt + j);
+    uint32_t parity = 0;
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+        for (int c = 0; c < 8; ++c) {
+            uint32_t h[4], l[4];
+            for (int j = 0; j < 4; ++j) split_tf32(v[c * 4 + j], h[j], l[j]);
+            *reinterpret_cast<uint4*>(Ahi + sw128(gt, c)) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(Alo + sw128(gt, c)) = make_uint4(l[0], l[1], l[2], l[3]);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        asm volatile("bar.sync %0, 128;" :: "r"(grp + 1) : "memory");
+        if (gt == 0) {
+            tc_fence_after();
+            constexpr uint32_t idesc = make_idesc(128, 32);
+            for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t ah = make_desc(smem_u32(Ahi) + ks * 32), al = make_desc(smem_u32(Alo) + ks * 32);
+                const uint64_t bh = make_desc(smem_u32(Bhi) + ks * 32), bl = make_desc(smem_u32(Blo) + ks * 32);
+                umma_tf32_ss(tbase, al, bh, idesc, ks > 0);
+                umma_tf32_ss(tbase, ah, bl, idesc, 1);
+                umma_tf32_ss(tbase, ah, bh, idesc, 1);
+            }
+            umma_commit(&bar[grp]);
+        }
+        mbar_wait(&bar[grp], parity);
+        parity ^= 1;
+        tc_fence_after();
+        tmem_ld32(tbase + lane_base, v);
+        for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j] * 0.01f, 0.f), 8.f) + 0.125f;
+    }
+    const long long t1 = clock64();
+    float s = 0.f;
+    for (int j = 0; j < 32; ++j) s += v[j];
+    out[blockIdx.x * blockDim.x + tid] = s;
+    if (tid == 0) cycles[blockIdx.x] = t1 - t0;
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tslot, 64 * G >= 32 ? 64 * G : 32);
+}
+
+template <int G>
+static void run_phase(int grid) {
+    float* out; long long* cyc;
+    CK(cudaMalloc(&out, grid * 128 * G * 4)); CK(cudaMalloc(&cyc, grid * 8));
+    const size_t smem = 1024 + G * 32768 + 8192;
+    CK(cudaFuncSetAttribute(phase_probe<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int iters = 2000;
+    phase_probe<G><<<grid, 128 * G, smem>>>(out, cyc, iters);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0));
+    phase_probe<G><<<grid, 128 * G, smem>>>(out, cyc, iters);
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    long long c0; CK(cudaMemcpy(&c0, cyc, 8, cudaMemcpyDeviceToHost));
+    printf("phase probe: groups/CTA=%d grid=%d: %.1f cycles per phase per group-iteration (CTA 0), kernel %.3f ms -> %.1f ns per iteration\n",
+           G, grid, (double)c0 / iters, ms, ms * 1e6 / iters);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// MMA pipe rate: one thread issues `rounds` x 12 MMAs (M=128, K=8 each) back to back, then one commit; cycles from the
+// first issue to the mbarrier completion.  TS = A operand in TMEM, SS = A operand in shared memory.
+template <int N, bool TS>
+__global__ void __launch_bounds__(128) rate_probe(long long* cycles, int rounds) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tslot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    uint8_t* A = smem;                 // [128][32]
+    uint8_t* B = smem + 16384;         // [N][32]
+    for (int idx = tid; idx < (16384 + N * 128) / 4; idx += 128) reinterpret_cast<uint32_t*>(smem)[idx] = rna_tf32(0.001f * (idx % 97));
+    if (warp == 0) tmem_alloc(&tslot, 256);
+    if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = tslot;
+    {
+        uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int c = 0; c < 64; c += 8) tmem_st8(tbase + ((uint32_t)(warp * 32) << 16) + 128 + c, z);
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+        tc_fence_after();
+        constexpr uint32_t idesc = make_idesc(128, N);
+        const long long t0 = clock64();
+        for (int r = 0; r < rounds; ++r)
+            for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t ad = make_desc(smem_u32(A) + ks * 32), bd = make_desc(smem_u32(B) + ks * 32);
+                for (int rep = 0; rep < 3; ++rep) {
+                    if (TS) umma_tf32_ts(tbase, tbase + 128 + ks * 8 + (rep == 0 ? 32 : 0), bd, idesc, 1);
+                    else umma_tf32_ss(tbase, ad, bd, idesc, 1);
+                }
+            }
+        const long long t1 = clock64();
+        umma_commit(&bar);
+        mbar_wait(&bar, 0);
+        const long long t2 = clock64();
+        cycles[0] = t1 - t0;
+        cycles[1] = t2 - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, 256);
+}
+template <int N, bool TS>
+static void run_rate() {
+    long long* cyc; CK(cudaMalloc(&cyc, 16));
+    const size_t smem = 1024 + 16384 + N * 128;
+    CK(cudaFuncSetAttribute(rate_probe<N, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int rounds : {1, 4, 64}) {
+        rate_probe<N, TS><<<1, 128, smem>>>(cyc, rounds);
+        CK(cudaGetLastError());
+        CK(cudaDeviceSynchronize());
+        long long c[2]; CK(cudaMemcpy(c, cyc, 16, cudaMemcpyDeviceToHost));
+        printf("rate probe %s N=%d: %d MMAs: issue %lld cycles, issue+complete %lld cycles -> %.1f cycles per MMA\n", TS ? "TS" : "SS", N,
+               rounds * 12, c[0], c[1], (double)c[1] / (rounds * 12));
+    }
+}
+
+int main(int argc, char** argv) {
+    const int test = argc > 1 ? atoi(argv[1]) : 1;
+    switch (test) {
+        case 1: return run_gemm<32, 32, 0>("1xTF32 SS");
+        case 2: return run_gemm<32, 32, 1>("3xTF32 SS");
+        case 3: return run_gemm<64, 64, 1>("3xTF32 SS K=64 N=64");
+        case 4: return run_gemm<32, 32, 2>("3xTF32 TS (A in TMEM)");
+        case 5: run_phase<1>(1); run_phase<2>(1); run_phase<1>(148); run_phase<2>(148); run_phase<1>(296); return 0;
+        case 8: run_rate<32, true>(); run_rate<32, false>(); run_rate<64, true>(); run_rate<64, false>(); return 0;
+        case 6: return run_gemm<32, 64, 1>("3xTF32 SS K=32 N=64");
+        case 7: return run_gemm<64, 32, 1>("3xTF32 SS K=64 N=32");
+    }
+    return 0;
+}
