@@ -367,6 +367,146 @@ __global__ void __launch_bounds__(128) rate_probe(long long* cycles, int rounds)
     __syncthreads();
     if (warp == 0) tmem_dealloc(tbase, 256);
 }
+// Same measurement with warp-uniform operands (no divergence "waterfall" around UTCHMMA): one warp issues (lane 0),
+// optionally HAMMER other warps stream LDS.128 from shared memory at the same time (contention for the B-operand fetch).
+template <int N, bool TS, int HAMMER>
+__global__ void __launch_bounds__(32 * (1 + HAMMER)) rate2_probe(long long* cycles, float* sink, int rounds) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tslot;
+    __shared__ volatile int done;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const uint32_t base = __shfl_sync(0xffffffffu, (smem_u32(smem_raw) + 1023u) & ~1023u, 0);
+    for (int idx = tid; idx < (32768 + N * 128) / 4; idx += blockDim.x)
+        asm volatile("st.shared.b32 [%0], %1;" :: "r"(base + idx * 4), "r"(rna_tf32(0.001f * (idx % 97))) : "memory");
+    if (warp == 0) tmem_alloc(&tslot, 256);
+    if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); done = 0; }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = __shfl_sync(0xffffffffu, tslot, 0);
+    if (warp == 0) {
+        uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int c = 0; c < 64; c += 8) tmem_st8(tbase + 128 + c, z);      // lane quadrant 0 only (timing probe: the other lanes hold garbage)
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+            tc_fence_after();
+            constexpr uint32_t idesc = make_idesc(128, N);
+            const long long t0 = clock64();
+            for (int r = 0; r < rounds; ++r) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint64_t ad = make_desc(base + ks * 32), bd = make_desc(base + 32768 + ks * 32);
+#pragma unroll
+                    for (int rep = 0; rep < 3; ++rep) {
+                        if (TS) umma_tf32_ts(tbase, tbase + 128 + ks * 8 + (rep == 0 ? 32 : 0), bd, idesc, 1);
+                        else umma_tf32_ss(tbase, ad, bd, idesc, 1);
+                    }
+                }
+            }
+            const long long t1 = clock64();
+            umma_commit(&bar);
+            mbar_wait(&bar, 0);
+            const long long t2 = clock64();
+            cycles[0] = t1 - t0;
+            cycles[1] = t2 - t0;
+            done = 1;
+        }
+        __syncwarp();
+    } else {
+        float acc = 0.f;
+        uint32_t addr = base + 16384 + (tid & 127) * 16;
+        while (!done) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float4 v;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr + i * 2048));
+                acc += v.x + v.y + v.z + v.w;
+            }
+        }
+        sink[tid] = acc;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, 256);
+}
+// W warps issue concurrently, each into its own accumulator / A columns (the kernel's situation: one issuer per group).
+// MODE 0: chains of 12 accumulating MMAs; MODE 1: every MMA followed by its own commit (completion latency of singles)
+template <int N, int W>
+__global__ void __launch_bounds__(32 * W) rate3_probe(long long* cycles, int rounds) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ uint64_t bar[W];
+    __shared__ uint32_t tslot;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const uint32_t base = __shfl_sync(0xffffffffu, (smem_u32(smem_raw) + 1023u) & ~1023u, 0);
+    for (int idx = tid; idx < (W * N * 128) / 4; idx += blockDim.x)
+        asm volatile("st.shared.b32 [%0], %1;" :: "r"(base + idx * 4), "r"(rna_tf32(0.001f * (idx % 97))) : "memory");
+    if (warp == 0) tmem_alloc(&tslot, 512);
+    if (tid == 0) { for (int w = 0; w < W; ++w) mbar_init(&bar[w], 1); fence_mbar_init(); }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = __shfl_sync(0xffffffffu, tslot, 0) + warp * 128;
+    const uint32_t bsm = base + warp * N * 128;
+    if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc(128, N);
+        const long long t0 = clock64();
+        for (int r = 0; r < rounds; ++r) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t bd = make_desc(bsm + ks * 32);
+#pragma unroll
+                for (int rep = 0; rep < 3; ++rep) umma_tf32_ts(tbase, tbase + 64 + ks * 8 + (rep == 0 ? 32 : 0), bd, idesc, 1);
+            }
+        }
+        const long long t1 = clock64();
+        umma_commit(&bar[warp]);
+        mbar_wait(&bar[warp], 0);
+        const long long t2 = clock64();
+        cycles[2 * warp] = t1 - t0;
+        cycles[2 * warp + 1] = t2 - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(__shfl_sync(0xffffffffu, tslot, 0), 512);
+}
+template <int N, int W>
+static void run_rate3() {
+    long long* cyc; CK(cudaMalloc(&cyc, 16 * W));
+    const size_t smem = 1024 + W * N * 128;
+    CK(cudaFuncSetAttribute(rate3_probe<N, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int rounds : {1, 8, 64}) {
+        rate3_probe<N, W><<<1, 32 * W, smem>>>(cyc, rounds);
+        CK(cudaGetLastError());
+        CK(cudaDeviceSynchronize());
+        long long c[2 * W]; CK(cudaMemcpy(c, cyc, 16 * W, cudaMemcpyDeviceToHost));
+        long long mx = 0; for (int w = 0; w < W; ++w) mx = c[2 * w + 1] > mx ? c[2 * w + 1] : mx;
+        printf("rate3 TS N=%d issuing-warps=%d: %d MMAs per warp: warp0 issue %lld, slowest complete %lld cycles -> %.1f cycles per MMA (aggregate)\n", N, W,
+               rounds * 12, c[0], mx, (double)mx / (rounds * 12 * W));
+    }
+}
+
+template <int N, bool TS, int HAMMER>
+static void run_rate2() {
+    long long* cyc; float* sink; CK(cudaMalloc(&cyc, 16)); CK(cudaMalloc(&sink, 4096 * 4));
+    const size_t smem = 1024 + 32768 + N * 128;
+    CK(cudaFuncSetAttribute(rate2_probe<N, TS, HAMMER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int rounds : {1, 8, 64}) {
+        rate2_probe<N, TS, HAMMER><<<1, 32 * (1 + HAMMER), smem>>>(cyc, sink, rounds);
+        CK(cudaGetLastError());
+        CK(cudaDeviceSynchronize());
+        long long c[2]; CK(cudaMemcpy(c, cyc, 16, cudaMemcpyDeviceToHost));
+        printf("rate2 %s N=%d hammer-warps=%d: %d MMAs: issue %lld cycles, issue+complete %lld cycles -> %.1f cycles per MMA\n", TS ? "TS" : "SS", N, HAMMER,
+               rounds * 12, c[0], c[1], (double)c[1] / (rounds * 12));
+    }
+}
+
 template <int N, bool TS>
 static void run_rate() {
     long long* cyc; CK(cudaMalloc(&cyc, 16));
@@ -391,6 +531,9 @@ int main(int argc, char** argv) {
         case 4: return run_gemm<32, 32, 2>("3xTF32 TS (A in TMEM)");
         case 5: run_phase<1>(1); run_phase<2>(1); run_phase<1>(148); run_phase<2>(148); run_phase<1>(296); return 0;
         case 8: run_rate<32, true>(); run_rate<32, false>(); run_rate<64, true>(); run_rate<64, false>(); return 0;
+        case 9: run_rate2<32, true, 0>(); run_rate2<64, true, 0>(); run_rate2<32, false, 0>(); run_rate2<64, false, 0>();
+                run_rate2<64, true, 8>(); run_rate2<64, true, 15>(); run_rate2<32, true, 15>(); return 0;
+        case 10: run_rate3<64, 1>(); run_rate3<64, 2>(); run_rate3<64, 4>(); run_rate3<32, 4>(); run_rate3<128, 1>(); run_rate3<256, 1>(); return 0;
         case 6: return run_gemm<32, 64, 1>("3xTF32 SS K=32 N=64");
         case 7: return run_gemm<64, 32, 1>("3xTF32 SS K=64 N=32");
     }
