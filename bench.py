@@ -353,7 +353,7 @@ def main():
     ap.add_argument('--batch', type=int, default=4096)
     ap.add_argument('--humans', type=int, default=5)
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--streams', type=int, default=3, help='CUDA streams the independent steps are issued on')
+    ap.add_argument('--streams', type=int, default=4, help='CUDA streams the independent steps are issued on')
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', 0))

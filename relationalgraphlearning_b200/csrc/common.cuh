@@ -57,10 +57,10 @@ constexpr int MOTION_FLOATS = M_B1 + 8;
 // Every weight matrix is a B operand of tcgen05.mma kind::tf32: [n rows][32 k] K-major tiles in the UMMA
 // SWIZZLE_128B canonical layout (row = 128 B, 16-byte chunk c of row r stored at chunk c ^ (r & 7)), split into a
 // tf32 "hi" tile and a tf32 "lo" tile (w = hi + lo to ~2^-22) for the 3xTF32 product.  Offsets in floats.
-constexpr int T_W0   = 0;                       // emb layer 1, robot and human weights concatenated along k:
-                                                //   [64 hidden][k: 0-8 robot feats, 9-13 human feats, 14 robot bias, 15 human bias, 16-31 zero]
-                                                //   hi [64][32], lo at +2048
-constexpr int T_W1   = T_W0 + 4096;             // emb layer 2, stacked along n: rows 0-31 = w_h.2.weight, rows 32-63 = w_r.2.weight;
+constexpr int T_W0   = 0;                       // emb layer 1, robot and human weights concatenated along k, ONE [64 hidden][32] tile:
+                                                //   k 0-15 = hi of [0-8 robot feats, 9-13 human feats, 14 robot bias, 15 human bias],
+                                                //   k 16-31 = lo of the same 16 columns (the lo descriptor starts 64 B into the rows)
+constexpr int T_W1   = T_W0 + 2048;             // emb layer 2, stacked along n: rows 0-31 = w_h.2.weight, rows 32-63 = w_r.2.weight;
                                                 //   two k atoms: hi atoms at +0, +2048; lo atoms at +4096, +6144
 constexpr int T_WA   = T_W1 + 8192;             // layer-0 tile, stacked along n: rows 0-31 = w_a^T, rows 32-63 = Ws[0]^T (one N=64 MMA gives
                                                 //   Y = X w_a and X Ws[0] from a single A operand): hi [64][32], lo at +2048

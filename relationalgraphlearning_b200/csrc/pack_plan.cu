@@ -38,10 +38,12 @@ __device__ __forceinline__ void tc_put(float* tile, int lo_off, int row, int k, 
 }
 
 __device__ void pack_graph_tc(const RglGraphParams& p, float* tc, int t, int nt) {
-    for (int idx = t; idx < HID * 32; idx += nt) {          // emb layer 1: k-concatenated robot | human | biases
-        const int u = idx >> 5, k = idx & 31;
-        const float w = k < RD ? p.wr0_w[u * RD + k] : k < RD + HD ? p.wh0_w[u * HD + (k - RD)] : k == 14 ? p.wr0_b[u] : k == 15 ? p.wh0_b[u] : 0.f;
-        tc_put(tc + T_W0, 2048, u, k, w);
+    for (int idx = t; idx < HID * 16; idx += nt) {          // emb layer 1: k-concatenated robot | human | biases; hi at k, lo at k + 16
+        const int u = idx >> 4, k = idx & 15;
+        const float w = k < RD ? p.wr0_w[u * RD + k] : k < RD + HD ? p.wh0_w[u * HD + (k - RD)] : k == 14 ? p.wr0_b[u] : p.wh0_b[u];
+        const float hi = rna_tf32f(w);
+        tc[T_W0 + u * 32 + ((((k >> 2) ^ u) & 7) << 2) + (k & 3)] = hi;
+        tc[T_W0 + u * 32 + (((((k + 16) >> 2) ^ u) & 7) << 2) + (k & 3)] = rna_tf32f(w - hi);
     }
     for (int idx = t; idx < 64 * HID; idx += nt) {          // emb layer 2: n-stacked human (rows 0-31) | robot (rows 32-63)
         const int row = idx / HID, k = idx - row * HID;
