@@ -43,7 +43,7 @@ size_t rgl_packed_graph_floats(int num_layer) {
     if (num_layer < 1 || num_layer > RGL_MAX_LAYERS) return 0;
     return (size_t)rgl::graph_floats_total(num_layer);
 }
-size_t rgl_packed_value_floats(void) { return rgl::VALUE_FLOATS; }
+size_t rgl_packed_value_floats(void) { return rgl::VALUE_FLOATS_TOTAL; }
 size_t rgl_packed_motion_floats(void) { return rgl::MOTION_FLOATS_TOTAL; }
 
 int rgl_pack_graph(const RglGraphParams* p, float* packed, rgl_stream_t stream) {
@@ -109,7 +109,13 @@ int rgl_value_head(const float* E, int B, const float* value_packed, float* V, r
     if (B == 0) return RGL_OK;
     DevInfo d;
     if (int rc = dev_info(&d)) return rc;
-    cudaError_t e = rgl::run_value_head(E, B, value_packed, V, nullptr, nullptr, nullptr, aligned16(E) ? 1 : 0, d.sms, (cudaStream_t)stream);
+    // Large batches run the value network on tcgen05 (3xTF32, value_head_tc.cu); below ~one tile of 128 states per SM the
+    // fp32-FMA kernel has the lower latency (the tensor-core kernel stages 150 KB of weight tiles per CTA).
+    // RGL_VALUE_VARIANT (experiments only): 't' / 'f' force one of them.
+    static const char* variant = getenv("RGL_VALUE_VARIANT");
+    const bool tc = aligned16(E) && (variant ? variant[0] == 't' : B >= 128 * d.sms);
+    cudaError_t e = tc ? rgl::run_value_head_tc(E, B, value_packed, V, d.sms, d.max_smem, (cudaStream_t)stream)
+                       : rgl::run_value_head(E, B, value_packed, V, nullptr, nullptr, nullptr, aligned16(E) ? 1 : 0, d.sms, (cudaStream_t)stream);
     return e == cudaSuccess ? RGL_OK : fail_cuda(e, "rgl_value_head");
 }
 

@@ -76,6 +76,17 @@ constexpr int TM_B1 = TM_W1 + 320;              // [8] (5 used)
 constexpr int TMOTION_FLOATS = 4608;            // 18 KB
 constexpr int MOTION_TC_OFF = (MOTION_FLOATS + 63) & ~63;
 constexpr int MOTION_FLOATS_TOTAL = MOTION_TC_OFF + TMOTION_FLOATS;
+// value network mlp(32,[32,100,100,1]) for value_head_tc.cu: 100-wide layers padded to N = 112 (UMMA N % 16 == 0), the
+// K = 100 contraction of layer 2 split into four 32-wide k atoms (the last one carries 8 values: one k-step)
+constexpr int TV_NP   = 112;
+constexpr int TV_W0   = 0;                      // 0.weight [32][32]: hi, lo at +1024
+constexpr int TV_BIAS = 2048;                   // b0 [32] | b1 [128] at +32 | b2 [128] at +160 | 6.weight [128] at +288 | 6.bias [4] at +416
+constexpr int TV_W1   = TV_BIAS + 512;          // 2.weight [112][32] (rows 100-111 zero): hi, lo at +3584
+constexpr int TV_W2   = TV_W1 + 2 * TV_NP * 32; // 4.weight: hi atoms [112][32] at +a*3584 (k = 32a .. 32a+31), lo atoms at +14336
+constexpr int TVALUE_FLOATS = TV_W2 + 8 * TV_NP * 32;      // 38 400 floats = 150 KB
+constexpr int VALUE_TC_OFF = (VALUE_FLOATS + 63) & ~63;
+constexpr int VALUE_FLOATS_TOTAL = VALUE_TC_OFF + TVALUE_FLOATS;
+static_assert((TV_W1 * 4) % 1024 == 0 && (TV_W2 * 4) % 1024 == 0 && (TV_NP * 128) % 1024 == 0, "UMMA tiles are 1 KB aligned");
 static_assert(TM_B1 + 8 <= TMOTION_FLOATS && tc_graph_floats(1) % 256 == 0, "tensor-core blob sections are 1 KB multiples");
 
 static_assert(graph_floats(2) - (2 * HID + 3 * XD) * (LDW - XD) == 8256, "graph parameter count (SURVEY.md 2b) + row padding");

@@ -23,110 +23,10 @@
 //             rows read from the group's swizzled shared-memory buffer; attention weights never leave registers.
 #include <stdlib.h>
 #include "kernels.h"
+#include "tc_common.cuh"
 
 namespace rgl {
 
-// ------------------------------------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(slot)), "r"(cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(addr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
-}
-// D[tmem] (+)= A[tmem] * B[smem]^T, kind::tf32, issued by one thread for the whole CTA
-__device__ __forceinline__ void umma_tf32_ts(uint32_t d, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-        :: "r"(d), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
-}
-// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor, sm_100 version 1)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-}
-// instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, tf32 x tf32, both K-major, M x N
-__host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-#define RGL_R8(r, o)  "=r"(r[o]), "=r"(r[o + 1]), "=r"(r[o + 2]), "=r"(r[o + 3]), "=r"(r[o + 4]), "=r"(r[o + 5]), "=r"(r[o + 6]), "=r"(r[o + 7])
-#define RGL_I8(r, o)  "r"(r[o]), "r"(r[o + 1]), "r"(r[o + 2]), "r"(r[o + 3]), "r"(r[o + 4]), "r"(r[o + 5]), "r"(r[o + 6]), "r"(r[o + 7])
-// this thread's TMEM lane, 32 consecutive columns -> registers (load + wait in one asm block: results are defined after it)
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
-        "tcgen05.wait::ld.sync.aligned;"
-        : RGL_R8(r, 0), RGL_R8(r, 8), RGL_R8(r, 16), RGL_R8(r, 24)
-        : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&r)[32], uint32_t (&q)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%64];\n\t"
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
-        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%65];\n\t"
-        "tcgen05.wait::ld.sync.aligned;"
-        : RGL_R8(r, 0), RGL_R8(r, 8), RGL_R8(r, 16), RGL_R8(r, 24), RGL_R8(q, 0), RGL_R8(q, 8), RGL_R8(q, 16), RGL_R8(q, 24)
-        : "r"(taddr), "r"(taddr + 32) : "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-                 :: "r"(taddr), RGL_I8(r, 0), RGL_I8(r, 8) : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-// A-operand row: 16 / 32 values -> tf32 hi / lo columns of this thread's TMEM lane.  hi = x rounded to nearest tf32
-// (integer add of half an ulp, then mask: cvt.rna.tf32 is emulated with 3 instructions on sm_100), lo = x - hi exactly;
-// the tensor core drops the low 13 bits of lo (2^-23 relative to x).
-template <int NV>
-__device__ __forceinline__ void st_split(uint32_t t_hi, uint32_t t_lo, const float (&v)[NV]) {
-#pragma unroll
-    for (int b = 0; b < NV; b += 16) {
-        uint32_t hi[16], lo[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            hi[j] = (__float_as_uint(v[b + j]) + 0x1000u) & 0xffffe000u;
-            lo[j] = __float_as_uint(v[b + j] - __uint_as_float(hi[j]));
-        }
-        tmem_st16(t_hi + b, hi);
-        tmem_st16(t_lo + b, lo);
-    }
-}
-
-// one elected thread: D[128 x N] (+)= A * W^T over KS k-steps of 8, 3xTF32 (small terms first).  Every operand is
-// warp-uniform (derived from __shfl_sync(.., 0) values), so each MMA is one UTCHMMA with uniform-register operands.
-template <int KS>
-__device__ __forceinline__ void issue_gemm(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t w_hi, uint32_t w_lo, uint32_t idesc, uint32_t acc) {
-#pragma unroll
-    for (int ks = 0; ks < KS; ++ks) {
-        const uint64_t bh = umma_desc(w_hi + ks * 32), bl = umma_desc(w_lo + ks * 32);
-        umma_tf32_ts(d, a_lo + ks * 8, bh, idesc, acc);
-        umma_tf32_ts(d, a_hi + ks * 8, bl, idesc, 1);
-        umma_tf32_ts(d, a_hi + ks * 8, bh, idesc, 1);
-        acc = 1;
-    }
-}
-
-// shared memory through 32-bit addresses (one LOP3 per swizzled access instead of 64-bit generic pointer arithmetic)
-__device__ __forceinline__ float4 lds128s(uint32_t saddr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
-    return v;
-}
-__device__ __forceinline__ void sts128s(uint32_t saddr, float4 v) {
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
 // [128][32] fp32 row buffer, swizzled like the UMMA SWIZZLE_128B tiles (chunk c of row r at chunk c ^ (r & 7)): row-per-thread
 // LDS/STS.128 are conflict-free.  row_ptr() = address of the row with its swizzle phase folded in; chunk c = row_ptr ^ (c << 4).
 __device__ __forceinline__ uint32_t row_ptr(uint32_t xf_s, int row) { return xf_s + row * 128 + ((row & 7) << 4); }

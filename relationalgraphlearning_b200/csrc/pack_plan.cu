@@ -85,6 +85,27 @@ __global__ void pack_value_kernel(RglValueParams p, float* out) {
     pack_copy(out + V_B2, p.b2, VH, VHP, t, nt);
     pack_copy(out + V_W3, p.w3, VH, VHP, t, nt);
     pack_copy(out + V_B3, p.b3, 1, 4, t, nt);
+    // tensor-core section (common.cuh TV_*): Linear weights are [out,in] = B-operand rows already
+    float* tc = out + VALUE_TC_OFF;
+    for (int idx = t; idx < XD * XD; idx += nt) tc_put(tc + TV_W0, 1024, idx >> 5, idx & 31, p.w0[idx]);
+    for (int idx = t; idx < TV_NP * 32; idx += nt) {
+        const int r = idx >> 5, k = idx & 31;
+        tc_put(tc + TV_W1, TV_NP * 32, r, k, r < VH ? p.w1[r * XD + k] : 0.f);
+        for (int a = 0; a < 4; ++a) {
+            const int kk = 32 * a + k;
+            tc_put(tc + TV_W2 + a * TV_NP * 32, 4 * TV_NP * 32, r, k, (r < VH && kk < VH) ? p.w2[r * VH + kk] : 0.f);
+        }
+    }
+    float* b = tc + TV_BIAS;
+    for (int idx = t; idx < 512; idx += nt) {
+        float v = 0.f;
+        if (idx < 32) v = p.b0[idx];
+        else if (idx < 160) v = idx - 32 < VH ? p.b1[idx - 32] : 0.f;
+        else if (idx < 288) v = idx - 160 < VH ? p.b2[idx - 160] : 0.f;
+        else if (idx < 416) v = idx - 288 < VH ? p.w3[idx - 288] : 0.f;
+        else if (idx == 416) v = p.b3[0];
+        b[idx] = v;
+    }
 }
 
 __global__ void pack_motion_kernel(RglMotionParams p, float* out) {
