@@ -100,6 +100,15 @@ def cpu_reference_rate(workload, batch, nh, steps, warmup, budget_s=150.0):
     """states/s of the oracle port (the reference's ATen op sequence) on the host cores."""
     from oracle import rgl_oracle as O
     from relationalgraphlearning_b200.synthetic import synthetic_states
+    # The oracle allocates ~20 MB of temporaries per step; with glibc's default thresholds every one of them is mmap'ed and
+    # page-faulted afresh (measured 2.3-2.6x slower).  Give the CPU leg its best case: keep freed memory in the heap.
+    try:
+        import ctypes
+        libc = ctypes.CDLL('libc.so.6')
+        libc.mallopt(-3, 1 << 30)       # M_MMAP_THRESHOLD
+        libc.mallopt(-1, 1 << 30)       # M_TRIM_THRESHOLD
+    except Exception:  # noqa: BLE001
+        pass
     g1, ve, g2, sp = build_modules(0)
     sd = [{k: v.detach().clone() for k, v in m.state_dict().items()} for m in (g1, ve.value_network, g2, sp.human_motion_predictor)]
     pool = [synthetic_states(batch, nh, seed=100 + i) for i in range(8)]

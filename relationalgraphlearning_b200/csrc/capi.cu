@@ -109,11 +109,10 @@ int rgl_value_head(const float* E, int B, const float* value_packed, float* V, r
     if (B == 0) return RGL_OK;
     DevInfo d;
     if (int rc = dev_info(&d)) return rc;
-    // Large batches run the value network on tcgen05 (3xTF32, value_head_tc.cu); below ~one tile of 128 states per SM the
-    // fp32-FMA kernel has the lower latency (the tensor-core kernel stages 150 KB of weight tiles per CTA).
-    // RGL_VALUE_VARIANT (experiments only): 't' / 'f' force one of them.
+    // Inference runs the value network on tcgen05 (3xTF32, value_head_tc.cu): faster than the fp32-FMA kernel at every batch
+    // size (6.6 vs 8.1 us at B = 4096, 16 vs 92 us at B = 65536).  RGL_VALUE_VARIANT (experiments only): 't' / 'f' force one.
     static const char* variant = getenv("RGL_VALUE_VARIANT");
-    const bool tc = aligned16(E) && (variant ? variant[0] == 't' : B >= 128 * d.sms);
+    const bool tc = aligned16(E) && (variant ? variant[0] == 't' : true);
     cudaError_t e = tc ? rgl::run_value_head_tc(E, B, value_packed, V, d.sms, d.max_smem, (cudaStream_t)stream)
                        : rgl::run_value_head(E, B, value_packed, V, nullptr, nullptr, nullptr, aligned16(E) ? 1 : 0, d.sms, (cudaStream_t)stream);
     return e == cudaSuccess ? RGL_OK : fail_cuda(e, "rgl_value_head");
