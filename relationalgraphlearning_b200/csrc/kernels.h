@@ -39,6 +39,9 @@ cudaError_t run_sim_bwd(const float* A, const float* gA, const float* X, const f
                         cudaStream_t st);
 cudaError_t run_gcn_layer(const float* X, const float* A, const float* W, const float* wa, int B, int n, int flags,
                           float* Hout, float* Aout, int num_sms, size_t max_smem, cudaStream_t st);
+// tcgen05 variant (gcn_layer_tc.cu)
+cudaError_t run_gcn_layer_tc(const float* X, const float* A, const float* W, const float* wa, int B, int n, int flags,
+                             float* Hout, float* Aout, int num_sms, size_t max_smem, cudaStream_t st);
 cudaError_t run_pack_graph(const RglGraphParams& p, float* out, cudaStream_t st);
 cudaError_t run_pack_value(const RglValueParams& p, float* out, cudaStream_t st);
 cudaError_t run_pack_motion(const RglMotionParams& p, float* out, cudaStream_t st);

@@ -48,12 +48,27 @@ for nh, B, lw, skip in ((5, 20011, False, True), (1, 3000, False, True), (10, 90
     assert_close_scaled(H, Ho, 1e-5, tag + ':H')
     assert_close_scaled(V, Vo, 1e-5, tag + ':V')
     assert_close_scaled(S, So, 1e-5, tag + ':S')
+# stand-alone GCN layer (A given / computed in-kernel), several tiles per group and a ragged tail
+from relationalgraphlearning_b200 import ops
+for n, B in ((6, 30011), (11, 4001), (21, 4444), (2, 70001), (8, 515)):
+    g = torch.Generator().manual_seed(n)
+    X = torch.randn(B, n, 32, generator=g); W = torch.randn(32, 32, generator=g); wa = torch.randn(32, 32, generator=g) * 0.2
+    A = torch.softmax(torch.randn(B, n, n, generator=g), dim=2)
+    for skip in (False, True):
+        ref = torch.relu(torch.matmul(torch.matmul(A, X), W)) + (X if skip else 0)
+        got = ops.gcn_layer(X.to(dev), W.to(dev), A=A.to(dev), skip=skip)
+        assert_close_scaled(got, ref, 1e-5, 'gcn_A n%%d skip%%d' %% (n, skip))
+    Aref = torch.softmax(torch.matmul(torch.matmul(X, wa), X.transpose(1, 2)), dim=2)
+    ref = torch.relu(torch.matmul(torch.matmul(Aref, X), W)) + X
+    got, Agot = ops.gcn_layer(X.to(dev), W.to(dev), w_a=wa.to(dev), skip=True, return_A=True)
+    assert_close_scaled(got, ref, 1e-5, 'gcn_wa n%%d' %% n)
+    assert_close_scaled(Agot, Aref, 1e-5, 'gcn_wa A n%%d' %% n)
 print('variant ok')
 '''
 
 
 @pytest.mark.parametrize('env', [{'RGL_TC_GROUPS': '1'}, {'RGL_TC_GROUPS': '2'}, {'RGL_TC_GROUPS': '4'}, {},
-                                 {'RGL_GRAPH_VARIANT': 'm'}, {'RGL_GRAPH_VARIANT': '4'},
+                                 {'RGL_GRAPH_VARIANT': 'm'}, {'RGL_GRAPH_VARIANT': '4', 'RGL_GCN_VARIANT': 'f'},
                                  {'RGL_VALUE_VARIANT': 't', 'RGL_TC_VALUE_GROUPS': '1'}, {'RGL_VALUE_VARIANT': 't', 'RGL_TC_VALUE_GROUPS': '2'},
                                  {'RGL_VALUE_VARIANT': 'f'}],
                          ids=['tc_g1', 'tc_g2', 'tc_g4', 'tc_auto', 'legacy_mma', 'legacy_ffma', 'value_tc_g1', 'value_tc_g2', 'value_ffma'])
@@ -64,6 +79,7 @@ def test_kernel_variant_against_oracle(env):
     e.pop('RGL_TC_GROUPS', None)
     e.pop('RGL_GRAPH_VARIANT', None)
     e.pop('RGL_VALUE_VARIANT', None)
+    e.pop('RGL_GCN_VARIANT', None)
     e.pop('RGL_TC_VALUE_GROUPS', None)
     e.update(env)
     res = subprocess.run([sys.executable, '-c', CHILD % {'root': ROOT}], env=e, capture_output=True, text=True, timeout=240)
