@@ -577,11 +577,32 @@ def main():
         b1.record(hv.streams[0])
         barrier()
         extra_ms[1] = b0.elapsed_time(b1) / K2
-    times = torch.tensor([t_ms, e2e_ms] + extra_ms, dtype=torch.float64, device=dev)
+    # the one HBM-bound unit of the path: a stand-alone GCN layer on features resident in HBM, A given.
+    # 1 536 + 144 B per 6-node state; working set (1 M states = 1.7 GB) far beyond L2.
+    gcn_ms = 0.0
+    if args.workload == 'graph':
+        Bg, n_ = 1 << 20, nh + 1
+        Xg = torch.randn(Bg, n_, 32, device=dev)
+        Wg = torch.randn(32, 32, device=dev)
+        Ag = torch.softmax(torch.randn(Bg, n_, n_, device=dev), dim=2)
+        with torch.no_grad():
+            for _ in range(3):
+                ops.gcn_layer(Xg, Wg, A=Ag, skip=True)
+            barrier()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(10):
+                ops.gcn_layer(Xg, Wg, A=Ag, skip=True)
+            c1.record()
+        barrier()
+        gcn_ms = c0.elapsed_time(c1) / 10
+        del Xg, Ag
+    times = torch.tensor([t_ms, e2e_ms] + extra_ms + [gcn_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     t_ms, e2e_ms = float(times[0]), float(times[1])
     extra_ms = [float(times[2]), float(times[3])]
+    gcn_ms = float(times[4])
 
     if rank == 0:
         peaks = {}
@@ -626,6 +647,15 @@ def main():
             out['extra'] = {'value_path': {'call': 'ValueEstimator.forward = graph forward (E only) + value head -> V[B,1]',
                                            'value': world * B / (extra_ms[0] * 1e-3), 'e2e': world * B / (extra_ms[1] * 1e-3),
                                            'unit': 'states/s', 'd2h_bytes_per_step': B * 4}}
+        if gcn_ms > 0:
+            n_ = nh + 1
+            gb = (2 * 128 * n_ + 4 * n_ * n_) * (1 << 20) / (gcn_ms * 1e-3) / 1e9
+            out.setdefault('extra', {})['gcn_layer'] = {
+                'call': 'rgl_gcn_layer: H\' = relu(A (X W)) + X on features in HBM, A given, B = 1 Mi states per GPU (gcn_layer_tc_kernel)',
+                'value': world * (1 << 20) / (gcn_ms * 1e-3), 'unit': 'layer-states/s', 'launch_us': gcn_ms * 1e3,
+                'roofline': {'bound': 'hbm', 'achieved': gb, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': gb / hbm_peak,
+                             'algorithmic_bytes_per_state': 2 * 128 * n_ + 4 * n_ * n_,
+                             'note': 'the only unit of the path that sits at the HBM / FMA ridge (8.7 FLOP/B)'}}
         if world == 1 and not args.no_cpu_baseline:
             rate, cores, sample, ms, k = cpu_reference_rate(args.workload, B, nh, min(K, 2000), 3, budget_s=15.0)
             out['cpu_baseline'] = {'value': rate, 'unit': 'states/s', 'cores': cores, 'kind': 'port', 'sample': sample,

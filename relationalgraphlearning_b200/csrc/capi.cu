@@ -143,7 +143,7 @@ int rgl_gcn_layer(const float* X, const float* A, const float* W, const float* w
     if (int rc = dev_info(&d)) return rc;
     // tcgen05 kernel (3xTF32 X W, gcn_layer_tc.cu) unless RGL_GCN_VARIANT=f (experiments only) selects the fp32-FMA kernel
     static const char* variant = getenv("RGL_GCN_VARIANT");
-    const bool tc = variant ? variant[0] == 't' : true;
+    const bool tc = variant ? variant[0] != 'f' : true;
     cudaError_t e = tc ? rgl::run_gcn_layer_tc(X, A, W, w_a, B, n, flags, Hout, Aout, d.sms, d.max_smem, (cudaStream_t)stream)
                        : rgl::run_gcn_layer(X, A, W, w_a, B, n, flags, Hout, Aout, d.sms, d.max_smem, (cudaStream_t)stream);
     if (e == cudaErrorInvalidConfiguration) return fail(RGL_EUNSUPPORTED, "rgl_gcn_layer: tile does not fit in shared memory");

@@ -7,11 +7,26 @@
 //   operand in TMEM;  the per-state products run on the FMA pipe with the neighbours' rows in a swizzled shared-memory
 //   buffer;  the output tile (one contiguous HBM block) is staged and written as 512 contiguous bytes per warp instruction.
 //   The weight tiles (UMMA SWIZZLE_128B, hi / lo) are built in shared memory by the CTA from the nn.Parameter layout.
+#include <cuda.h>          // CUtensorMap (types only: cuTensorMapEncodeTiled is fetched through cudaGetDriverEntryPoint)
 #include <stdlib.h>
 #include "kernels.h"
 #include "tc_common.cuh"
 
 namespace rgl {
+
+// ---- TMA tensor copies (2-D tiles of the [rows][32] fp32 feature matrix, SWIZZLE_128B: the hardware lands the rows in
+// shared memory in exactly the chunk ^ (row & 7) pattern the UMMA tiles and the row-per-thread LDS/STS use) ----
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_s, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(dst_s), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, uint32_t src_s) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                 :: "l"(map), "r"(c0), "r"(c1), "r"(src_s) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t gl_row_ptr(uint32_t xf_s, int row) { return xf_s + row * 128 + ((row & 7) << 4); }
 
@@ -214,6 +229,260 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) gcn_layer_tc_kernel(c
     if (warp == 0) tmem_dealloc(tbase, 128 * G);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// TMA variant: the input tile (one contiguous block of SPT*n rows) is fetched by a 2-D tensor copy into a swizzled
+// shared-memory buffer, double-buffered one tile ahead, and the output tile leaves through a tensor store: no
+// row-per-thread global accesses (those cost one L1 wavefront per thread and put the LSU pipe at 82%).
+template <int N, int G>
+__global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) gcn_layer_tma_kernel(const __grid_constant__ CUtensorMap mapX,
+                                                                                  const __grid_constant__ CUtensorMap mapH,
+                                                                                  const float* __restrict__ Ag, const float* __restrict__ Wg,
+                                                                                  const float* __restrict__ wag, int B, int n_rt, int flags,
+                                                                                  float* __restrict__ Aout, int ntiles) {
+    constexpr int NMAX = N > 0 ? N : RGL_MAX_HUMANS + 1;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    float* tw = reinterpret_cast<float*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));   // hi [64][32] | lo [64][32]
+    float* buf_all = tw + 4096;                          // per group: in[0] | in[1] | xw   (3 x 16 KB, 1 KB aligned)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(buf_all + G * 3 * 4096);     // per group: mma, full[0], full[1]
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 3 * G);
+
+    const int n = N > 0 ? N : n_rt;
+    const int SPT = 128 / n;
+    const int tid = threadIdx.x, lane = tid & 31, gt = tid & 127;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int grp = warp >> 2, wq = warp & 3;
+    const bool skip = flags & RGL_FLAG_SKIP;
+    const bool sim = Ag == nullptr;
+
+    if (warp == 0) tmem_alloc(tslot, 128 * G);
+    if (tid == 0) {
+        for (int i = 0; i < 3 * G; ++i) mbar_init(bars + i, 1);
+        fence_mbar_init();
+    }
+    for (int idx = tid; idx < (sim ? 2048 : 1024); idx += blockDim.x) {
+        const int m = idx >> 10, k = (idx >> 5) & 31, nn = idx & 31;
+        const float w = (sim && m == 0) ? __ldg(wag + k * XD + nn) : __ldg(Wg + k * XD + nn);
+        const int row = (sim ? m * 32 : 0) + nn;
+        const int o = row * 32 + ((((k >> 2) ^ row) & 7) << 2) + (k & 3);
+        const float hi = __uint_as_float((__float_as_uint(w) + 0x1000u) & 0xffffe000u);
+        tw[o] = hi;
+        tw[2048 + o] = w - hi;
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    const uint32_t tbase = __shfl_sync(0xffffffffu, *tslot, 0);
+    const uint32_t tg = tbase + grp * 128;
+    const uint32_t tl = tg + ((uint32_t)(wq * 32) << 16);
+    const uint32_t tw_s = __shfl_sync(0xffffffffu, smem_u32(tw), 0);
+    const uint32_t buf_s = __shfl_sync(0xffffffffu, smem_u32(buf_all), 0) + grp * 49152;
+    const uint32_t xw_s = buf_s + 32768;
+    uint64_t* gbar = bars + 3 * grp;
+    uint64_t* full = gbar + 1;
+    uint32_t par = 0;
+    const bool issuer = wq == 0;
+    auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" :: "r"(grp + 1) : "memory"); };
+    auto mma_wait = [&]() { mbar_wait(gbar, par); par ^= 1; tc_fence_after(); };
+    auto publish = [&]() { tmem_st_wait(); tc_fence_before(); group_sync(); };
+
+    const int s_loc = gt / n;
+    const bool row_used = gt < SPT * n;
+    const int srow0 = s_loc * n;
+    const int tstride = gridDim.x * G;
+    const int rows_tile = SPT * n;
+    const uint32_t tile_bytes = (uint32_t)rows_tile * 128u;
+
+    int tile = blockIdx.x * G + grp;
+    if (gt == 0 && tile < ntiles) {
+        mbar_arrive_expect_tx(full + 0, tile_bytes);
+        tma_load_2d(buf_s, &mapX, 0, tile * rows_tile, full + 0);
+    }
+    for (int it = 0; tile < ntiles; tile += tstride, ++it) {
+        const int b = it & 1;
+        const uint32_t in_s = buf_s + b * 16384;
+        const long s0 = (long)tile * SPT;
+        const int cnt = (int)min((long)SPT, (long)B - s0);
+        const bool valid = row_used && s_loc < cnt;
+        const long grow = s0 * n + gt;
+
+        // next tile's features -> the other input buffer (its last reader was the tensor store of tile it-1)
+        if (gt == 0 && tile + tstride < ntiles) {
+            tma_store_wait_read();
+            mbar_arrive_expect_tx(full + (b ^ 1), tile_bytes);
+            tma_load_2d(buf_s + (b ^ 1) * 16384, &mapX, 0, (tile + tstride) * rows_tile, full + (b ^ 1));
+        }
+        float p[NMAX];
+        if (!sim) {
+#pragma unroll
+            for (int j = 0; j < NMAX; ++j)
+                if (N > 0 || j < n) p[j] = valid ? __ldg(Ag + grow * n + j) : 0.f;
+            if (tile + tstride < ntiles && row_used) {
+                const long nrow = (long)(tile + tstride) * rows_tile + gt;
+                if (nrow < (long)B * n) asm volatile("prefetch.global.L2 [%0];" :: "l"(Ag + nrow * n));
+            }
+        }
+        mbar_wait(full + b, (it >> 1) & 1);
+        const uint32_t my_in = gl_row_ptr(in_s, gt), my_xw = gl_row_ptr(xw_s, gt);
+        float x[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float4 v = lds128s(my_in ^ (c << 4));
+            x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+        }
+        st_split<32>(tl + 64, tl + 96, x);
+        publish();
+        if (issuer) {
+            if (lane == 0) {
+                tc_fence_after();
+                if (sim) issue_gemm<4>(tg, tg + 64, tg + 96, tw_s, tw_s + 8192, umma_idesc(128, 64), 0);
+                else issue_gemm<4>(tg + 32, tg + 64, tg + 96, tw_s, tw_s + 8192, umma_idesc(128, 32), 0);
+                umma_commit(gbar);
+            }
+            __syncwarp();
+        }
+        mma_wait();
+
+        if (sim) {
+            uint32_t yr[32];
+            tmem_ld32(tl, yr);
+            if (row_used) {
+                float mx = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < NMAX; ++j) {
+                    if (N > 0 || j < n) {
+                        const uint32_t rp = gl_row_ptr(in_s, srow0 + j);
+                        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const float4 xv = lds128s(rp ^ (c << 4));
+                            d0 = fmaf(__uint_as_float(yr[4 * c + 0]), xv.x, d0);
+                            d1 = fmaf(__uint_as_float(yr[4 * c + 1]), xv.y, d1);
+                            d2 = fmaf(__uint_as_float(yr[4 * c + 2]), xv.z, d2);
+                            d3 = fmaf(__uint_as_float(yr[4 * c + 3]), xv.w, d3);
+                        }
+                        p[j] = (d0 + d1) + (d2 + d3);
+                        mx = fmaxf(mx, p[j]);
+                    }
+                }
+                float sum = 0.f;
+#pragma unroll
+                for (int j = 0; j < NMAX; ++j)
+                    if (N > 0 || j < n) { p[j] = expf(p[j] - mx); sum += p[j]; }
+#pragma unroll
+                for (int j = 0; j < NMAX; ++j)
+                    if (N > 0 || j < n) p[j] = p[j] / sum;
+            }
+        }
+        if (Aout != nullptr && valid) {
+#pragma unroll
+            for (int j = 0; j < NMAX; ++j)
+                if (N > 0 || j < n) Aout[grow * n + j] = p[j];
+        }
+
+        // ---- X W rows -> xw buffer;  H' = relu(sum_j A[i][j] (X W)[j]) (+ X) ----
+        {
+            uint32_t hw[32];
+            tmem_ld32(tl + 32, hw);
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                sts128s(my_xw ^ (c << 4), make_float4(__uint_as_float(hw[4 * c]), __uint_as_float(hw[4 * c + 1]),
+                                                      __uint_as_float(hw[4 * c + 2]), __uint_as_float(hw[4 * c + 3])));
+        }
+        tc_fence_before();
+        group_sync();                                    // X W rows visible; every similarity read of the input rows is done
+        float acc[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+        if (row_used) {
+#pragma unroll
+            for (int j = 0; j < NMAX; ++j) {
+                if (N > 0 || j < n) {
+                    const uint32_t rp = gl_row_ptr(xw_s, srow0 + j);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float4 hv = lds128s(rp ^ (c << 4));
+                        acc[4 * c + 0] = fmaf(p[j], hv.x, acc[4 * c + 0]);
+                        acc[4 * c + 1] = fmaf(p[j], hv.y, acc[4 * c + 1]);
+                        acc[4 * c + 2] = fmaf(p[j], hv.z, acc[4 * c + 2]);
+                        acc[4 * c + 3] = fmaf(p[j], hv.w, acc[4 * c + 3]);
+                    }
+                }
+            }
+        }
+        if (skip) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) x[c] += fmaxf(acc[c], 0.f);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) x[c] = fmaxf(acc[c], 0.f);
+        }
+        // ---- the output rows overwrite the (dead) input rows of this tile; one tensor store writes the block (rows beyond
+        // the batch are clipped by the tensor map) ----
+#pragma unroll
+        for (int c = 0; c < 8; ++c) sts128s(my_in ^ (c << 4), make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]));
+        fence_proxy_async();                             // generic-proxy stores -> visible to the TMA engine
+        group_sync();                                    // also: every read of the X W rows is done (next tile may overwrite xw)
+        if (gt == 0) tma_store_2d(&mapH, 0, tile * rows_tile, in_s);
+    }
+    if (gt == 0) tma_store_wait_all();                   // the stores must have read shared memory (and landed) before exit
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, 128 * G);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+// [rows][32] fp32 matrix, box = box_rows x 32, SWIZZLE_128B
+static bool make_row_map(CUtensorMap* m, const float* base, long rows, int box_rows) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    const cuuint64_t dims[2] = {32, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {128};
+    const cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int N, int G>
+static cudaError_t launch_gl_tma(const float* X, const float* A, const float* W, const float* wa, int B, int n, int flags, float* Hout,
+                                 float* Aout, int num_sms, size_t max_smem, cudaStream_t st) {
+    const size_t smem = 1024 + (4096 + (size_t)G * 3 * 4096) * 4 + 3 * G * 8 + 16;
+    if (smem > max_smem) return cudaErrorInvalidConfiguration;
+    const int spt = 128 / n;
+    CUtensorMap mx, mh;
+    if (!make_row_map(&mx, X, (long)B * n, spt * n) || !make_row_map(&mh, Hout, (long)B * n, spt * n)) return cudaErrorNotSupported;
+    static bool attr_set = false;     // benign race: idempotent
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gcn_layer_tma_kernel<N, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const int ntiles = (B + spt - 1) / spt;
+    int per_sm = (int)((228 * 1024) / (smem + 1024));
+    const int max_cta = G <= 2 ? 2 : 1;
+    if (per_sm > max_cta) per_sm = max_cta;
+    if (per_sm < 1) per_sm = 1;
+    const int want = (ntiles + G - 1) / G;
+    const int grid = want < num_sms * per_sm ? want : num_sms * per_sm;
+    gcn_layer_tma_kernel<N, G><<<grid, 128 * G, smem, st>>>(mx, mh, A, W, wa, B, n, flags, Aout, ntiles);
+    return cudaGetLastError();
+}
+
 template <int N, int G>
 static cudaError_t launch_gl(const float* X, const float* A, const float* W, const float* wa, int B, int n, int flags, float* Hout,
                              float* Aout, int num_sms, size_t max_smem, cudaStream_t st) {
@@ -241,6 +510,16 @@ static cudaError_t dispatch_gl(const float* X, const float* A, const float* W, c
     const int spt = 128 / n, ntiles = (B + spt - 1) / spt;
     int g = force ? atoi(force) : 0;
     if (g != 1 && g != 2 && g != 4) g = ntiles <= 2 * num_sms ? 1 : 2;
+    // RGL_GCN_VARIANT=l (experiments only): row-per-thread global loads / staged copy-out instead of the TMA tensor copies
+    static const char* variant = getenv("RGL_GCN_VARIANT");
+    if (!(variant && variant[0] == 'l')) {
+        // 48 KB of tile buffers per group: one CTA of four groups per SM in the steady state
+        if (!force) g = ntiles <= num_sms ? 1 : (ntiles <= 2 * num_sms ? 2 : 4);
+        cudaError_t e = g == 1 ? launch_gl_tma<N, 1>(X, A, W, wa, B, n, flags, Hout, Aout, num_sms, max_smem, st)
+                      : g == 2 ? launch_gl_tma<N, 2>(X, A, W, wa, B, n, flags, Hout, Aout, num_sms, max_smem, st)
+                               : launch_gl_tma<N, 4>(X, A, W, wa, B, n, flags, Hout, Aout, num_sms, max_smem, st);
+        if (e != cudaErrorNotSupported) return e;       // no tensor-map entry point in this driver: fall through
+    }
     if (g == 1) return launch_gl<N, 1>(X, A, W, wa, B, n, flags, Hout, Aout, num_sms, max_smem, st);
     if (g == 2) return launch_gl<N, 2>(X, A, W, wa, B, n, flags, Hout, Aout, num_sms, max_smem, st);
     return launch_gl<N, 4>(X, A, W, wa, B, n, flags, Hout, Aout, num_sms, max_smem, st);
