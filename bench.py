@@ -615,6 +615,7 @@ def main():
         ach_gbs = abytes * B / per_launch_s / 1e9
         ach_tf = aflops * B / per_launch_s / 1e12
         traffic, traffic_note = None, 'no ncu capture for this workload / batch'
+        tj = {}
         try:
             tj = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
             key = '%s_b%d_nh%d' % (args.workload, B, nh)
@@ -655,6 +656,7 @@ def main():
                 'value': world * (1 << 20) / (gcn_ms * 1e-3), 'unit': 'layer-states/s', 'launch_us': gcn_ms * 1e3,
                 'roofline': {'bound': 'hbm', 'achieved': gb, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': gb / hbm_peak,
                              'algorithmic_bytes_per_state': 2 * 128 * n_ + 4 * n_ * n_,
+                             'traffic': (tj.get('gcn_layer_b1048576_n%d' % n_) or {}).get('dram_bytes'),
                              'note': 'the only unit of the path that sits at the HBM / FMA ridge (8.7 FLOP/B)'}}
         if world == 1 and not args.no_cpu_baseline:
             rate, cores, sample, ms, k = cpu_reference_rate(args.workload, B, nh, min(K, 2000), 3, budget_s=15.0)
