@@ -652,7 +652,7 @@ def main():
             n_ = nh + 1
             gb = (2 * 128 * n_ + 4 * n_ * n_) * (1 << 20) / (gcn_ms * 1e-3) / 1e9
             out.setdefault('extra', {})['gcn_layer'] = {
-                'call': 'rgl_gcn_layer: H\' = relu(A (X W)) + X on features in HBM, A given, B = 1 Mi states per GPU (gcn_layer_tc_kernel)',
+                'call': 'rgl_gcn_layer: H\' = relu(A (X W)) + X on features in HBM, A given, B = 1 Mi states per GPU (gcn_layer_tma_kernel)',
                 'value': world * (1 << 20) / (gcn_ms * 1e-3), 'unit': 'layer-states/s', 'launch_us': gcn_ms * 1e3,
                 'roofline': {'bound': 'hbm', 'achieved': gb, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': gb / hbm_peak,
                              'algorithmic_bytes_per_state': 2 * 128 * n_ + 4 * n_ * n_,
