@@ -27,12 +27,15 @@
 
 namespace rgl {
 
-// [128][32] fp32 row buffer, swizzled like the UMMA SWIZZLE_128B tiles (chunk c of row r at chunk c ^ (r & 7)): row-per-thread
-// LDS/STS.128 are conflict-free.  row_ptr() = address of the row with its swizzle phase folded in; chunk c = row_ptr ^ (c << 4).
-__device__ __forceinline__ uint32_t row_ptr(uint32_t xf_s, int row) { return xf_s + row * 128 + ((row & 7) << 4); }
+// [128][32] fp32 row buffer of a group, rows padded to 36 floats (144 B = 4 banks past a multiple of 32): row-per-thread
+// LDS/STS.128 are conflict-free (8 consecutive rows cover all 32 banks) and every chunk address is row base + immediate
+// (the buffer is no MMA operand -- the A operand lives in TMEM -- so it does not need the UMMA swizzle).
+constexpr int XF_ROW = 144;                 // bytes
+constexpr int XF_GROUP = 128 * XF_ROW;      // 18 KB per group
+__device__ __forceinline__ uint32_t row_ptr(uint32_t xf_s, int row) { return xf_s + row * XF_ROW; }
 __device__ __forceinline__ void xf_store_row(uint32_t rp, const float (&v)[32]) {
 #pragma unroll
-    for (int c = 0; c < 8; ++c) sts128s(rp ^ (c << 4), make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
+    for (int c = 0; c < 8; ++c) sts128s(rp + c * 16, make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
 }
 
 // --------------------------------------------------------------------------------------------------- kernel
@@ -52,7 +55,7 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tc_kern
     float* tw = smem;                               // graph operand tiles (1024 B aligned)
     float* tm = tw + twf;                           // motion operand tiles (only when S is requested)
     float* xf_all = tm + (a.mw ? TMOTION_FLOATS : 0);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(xf_all + G * 4096);      // [0],[1] weights; [2+g] group g
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xf_all + G * (XF_GROUP / 4));      // [0],[1] weights; [2+g] group g
     uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 2 + G);
 
     const int tid = threadIdx.x, lane = tid & 31, gt = tid & 127;
@@ -82,7 +85,7 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tc_kern
     const uint32_t tbase = __shfl_sync(0xffffffffu, *tslot, 0);
     const uint32_t tg = tbase + grp * TC_COLS;                        // this group's TMEM columns (lane field 0: MMA view)
     const uint32_t tl = tg + ((uint32_t)(wq * 32) << 16);             // this warp's lane quadrant (ld / st view)
-    const uint32_t xf_s = __shfl_sync(0xffffffffu, smem_u32(xf_all), 0) + grp * 16384;
+    const uint32_t xf_s = __shfl_sync(0xffffffffu, smem_u32(xf_all), 0) + grp * XF_GROUP;
     uint64_t* gbar = bars + 2 + grp;
     uint32_t par = 0;
     const uint32_t tw_s = __shfl_sync(0xffffffffu, smem_u32(tw), 0), tm_s = __shfl_sync(0xffffffffu, smem_u32(tm), 0);   // warp-uniform for the compiler
@@ -255,7 +258,7 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tc_kern
                             float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
 #pragma unroll
                             for (int c = 0; c < 8; ++c) {
-                                const float4 xv = lds128s(rp ^ (c << 4));
+                                const float4 xv = lds128s(rp + c * 16);
                                 d0 = fmaf(__uint_as_float(yr[4 * c + 0]), xv.x, d0);
                                 d1 = fmaf(__uint_as_float(yr[4 * c + 1]), xv.y, d1);
                                 d2 = fmaf(__uint_as_float(yr[4 * c + 2]), xv.z, d2);
@@ -269,9 +272,10 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tc_kern
 #pragma unroll
                     for (int j = 0; j < NMAX; ++j)
                         if (N > 0 || j < n) { p[j] = expf(p[j] - mx); sum += p[j]; }
+                    const float rs = 1.f / sum;             // one division; p * (1/sum) differs from p / sum by <= 1 ulp
 #pragma unroll
                     for (int j = 0; j < NMAX; ++j)
-                        if (N > 0 || j < n) p[j] = p[j] / sum;
+                        if (N > 0 || j < n) p[j] *= rs;
                     if (a.A0 != nullptr && l == 0 && tile == 0 && s_loc == 0) {
 #pragma unroll
                         for (int j = 0; j < NMAX; ++j)
@@ -288,7 +292,7 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tc_kern
                 tmem_ld32(tl + C_D + 32, hw);
 #pragma unroll
                 for (int c = 0; c < 8; ++c)
-                    sts128s(my_row ^ (c << 4), make_float4(__uint_as_float(hw[4 * c]), __uint_as_float(hw[4 * c + 1]),
+                    sts128s(my_row + c * 16, make_float4(__uint_as_float(hw[4 * c]), __uint_as_float(hw[4 * c + 1]),
                                                            __uint_as_float(hw[4 * c + 2]), __uint_as_float(hw[4 * c + 3])));
             }
             tc_fence_before();
@@ -303,7 +307,7 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tc_kern
                         const uint32_t rp = row_ptr(xf_s, j == 0 ? s_loc : hbase + j - 1);
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
-                            const float4 hv = lds128s(rp ^ (c << 4));
+                            const float4 hv = lds128s(rp + c * 16);
                             acc[4 * c + 0] = fmaf(p[j], hv.x, acc[4 * c + 0]);
                             acc[4 * c + 1] = fmaf(p[j], hv.y, acc[4 * c + 1]);
                             acc[4 * c + 2] = fmaf(p[j], hv.z, acc[4 * c + 2]);
@@ -382,7 +386,7 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tc_kern
                 const int orow = idx >> 3, c = idx & 7;
                 const int s = orow / n, i = orow - s * n;
                 const int srow = i == 0 ? s : SPT + s * Nh + i - 1;
-                *reinterpret_cast<float4*>(dst + (size_t)idx * 4) = lds128s(row_ptr(xf_s, srow) ^ (c << 4));
+                *reinterpret_cast<float4*>(dst + (size_t)idx * 4) = lds128s(row_ptr(xf_s, srow) + c * 16);
             }
             // the next tile writes xf only after further group barriers: no extra barrier needed here
         }
@@ -397,7 +401,7 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tc_kern
 
 // ---------------------------------------------------------------------------------------------------
 static size_t tc_smem_bytes(int L, bool motion, int G) {
-    return 1024 + ((size_t)tc_graph_floats(L) + (motion ? TMOTION_FLOATS : 0) + (size_t)G * 4096) * 4 + (2 + G) * 8 + 16;
+    return 1024 + ((size_t)tc_graph_floats(L) + (motion ? TMOTION_FLOATS : 0) + (size_t)G * (XF_GROUP / 4)) * 4 + (2 + G) * 8 + 16;
 }
 
 template <int N, int G>
