@@ -294,14 +294,20 @@ def plan_bench(args, rank, world, local):
     pol.set_phase('test')
     pol.build_action_space(1.0)
     pool = [synthetic_states(E, nh, seed=900 + i + 100 * rank, device=dev) for i in range(4)]
-    run = (lambda r, h: pol.predict_batch_graphed(r, h)[0]) if args.plan_graph else pol.predict_batch
+    # predict() replays the whole look-ahead from a CUDA graph captured once per input shape (ModelPredictiveRL.use_cuda_graphs,
+    # the policy's default); --plan-eager issues the launches one by one from Python instead.
+    graphed = not args.plan_eager
+    run = (lambda r, h: pol.predict_batch_graphed(r, h)[0]) if graphed else pol.predict_batch
+    pol.stat_value_states = pol.stat_sp_states = 0
+    l0 = ops.LAUNCHES
+    pol.predict_batch(*pool[0])                      # one eager pass: launches and rollout states of one step
+    launches_per_step = ops.LAUNCHES - l0
+    rollout_per_step = pol.stat_value_states + pol.stat_sp_states
     for i in range(W):
         run(*pool[i % 4])
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    pol.stat_value_states = pol.stat_sp_states = 0
-    l0 = ops.LAUNCHES
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(K):
@@ -315,12 +321,12 @@ def plan_bench(args, rank, world, local):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
         ms = float(t[0])
-        rollout = (pol.stat_value_states + pol.stat_sp_states) / K
+        rollout = rollout_per_step
         out = {'metric': 'model_predictive_rl look-ahead: root states planned/sec (d=%d, w=%d, %d actions, %d humans)' %
                          (args.depth, args.width, len(pol.action_space), nh),
                'value': world * E * K / (ms * 1e-3), 'unit': 'root states/s', 'n_gpus': world, 'steps': K, 'warmup': W,
                'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-               'data': 'synthetic', 'gpu_launches': ops.LAUNCHES - l0,
+               'data': 'synthetic', 'gpu_launches': launches_per_step * K, 'graph_replay': graphed,
                'rollout_states_per_step': rollout, 'rollout_states_per_s': world * rollout * K / (ms * 1e-3),
                'config': {'workload': 'planner tree d=%d w=%d, %d root states per GPU' % (args.depth, args.width, E),
                           'parallelism': 'dp%d (root states sharded, no collective)' % world}}
@@ -354,7 +360,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='graph', choices=['graph', 'value', 'statepred', 'train', 'plan'])
     ap.add_argument('--roots', type=int, default=1024)
-    ap.add_argument('--plan-graph', action='store_true', help='replay the look-ahead from a captured CUDA graph')
+    ap.add_argument('--plan-eager', action='store_true', help='plan workload: launch from Python instead of replaying the captured CUDA graph')
     ap.add_argument('--depth', type=int, default=2)
     ap.add_argument('--width', type=int, default=2)
     ap.add_argument('--speed-samples', type=int, default=2)
@@ -362,6 +368,7 @@ def main():
     ap.add_argument('--batch', type=int, default=4096)
     ap.add_argument('--humans', type=int, default=5)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--host-depth', type=int, default=4, help='e2e: batches in flight through hostio.HostStream')
     ap.add_argument('--streams', type=int, default=4, help='CUDA streams the independent steps are issued on')
     args = ap.parse_args()
 
@@ -509,7 +516,7 @@ def main():
     npin = min(pool_n, 48)
     robots_p = [r.pin_memory() for r in robots[:npin]]
     humans_p = [h.pin_memory() for h in humans[:npin]]
-    depth = 3
+    depth = args.host_depth
     hs = HostStream(args.workload, module, B, nh, dev, depth=depth)
     for i in range(max(W, npin * depth)):            # warm-up also captures the per-(slot, buffer) graphs
         hs.submit(robots_p[i % npin], humans_p[i % npin])
