@@ -440,7 +440,9 @@ static cudaError_t dispatch_tc(const GraphArgs& a, int num_sms, size_t max_smem,
         // Small batches (at most two tiles per SM): one group per CTA so that the tiles spread over all SMs.
         // RGL_FLAG_THROUGHPUT (the caller keeps several launches in flight): two groups per CTA even for small batches, so
         // that concurrent launches share SMs at the steady-state occupancy (measured at B = 4096: 850 vs 677 M states/s).
-        g = a.mw != nullptr ? 4 : ((ntiles <= 2 * num_sms && !(a.flags & RGL_FLAG_THROUGHPUT)) ? 1 : 2);
+        // (with the motion tiles a one-group CTA still fits twice per SM: small state-predictor batches spread over all SMs)
+        if (a.mw != nullptr) g = ntiles <= 2 * num_sms ? 1 : 4;
+        else g = (ntiles <= 2 * num_sms && !(a.flags & RGL_FLAG_THROUGHPUT)) ? 1 : 2;
     }
     if (g == 1) return launch_tc<N, 1>(a, num_sms, max_smem, st);
     if (g == 2) return launch_tc<N, 2>(a, num_sms, max_smem, st);
