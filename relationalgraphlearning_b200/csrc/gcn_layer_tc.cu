@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) gcn_layer_tc_kernel(c
     uint32_t par = 0;
     const bool issuer = wq == 0;
     auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" :: "r"(grp + 1) : "memory"); };
-    auto mma_wait = [&]() { mbar_wait(gbar, par); par ^= 1; tc_fence_after(); };
+    auto mma_wait = [&]() { mbar_wait_sleepy(gbar, par); par ^= 1; tc_fence_after(); };
     auto publish = [&]() { tmem_st_wait(); tc_fence_before(); group_sync(); };
 
     const int s_loc = gt / n;
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) gcn_layer_tc_kernel(c
         st_split<32>(tl + 64, tl + 96, x);
         publish();
         if (issuer) {
-            if (lane == 0) {
+            if (elect_one()) {
                 tc_fence_after();
                 // with w_a: one N = 64 chain, columns [0,32) = Y = X w_a, [32,64) = X W; otherwise N = 32 into columns [32,64)
                 if (sim) issue_gemm<4>(tg, tg + 64, tg + 96, tw_s, tw_s + 8192, umma_idesc(128, 64), 0);
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) gcn_layer_tma_kernel(
     uint32_t par = 0;
     const bool issuer = wq == 0;
     auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" :: "r"(grp + 1) : "memory"); };
-    auto mma_wait = [&]() { mbar_wait(gbar, par); par ^= 1; tc_fence_after(); };
+    auto mma_wait = [&]() { mbar_wait_sleepy(gbar, par); par ^= 1; tc_fence_after(); };
     auto publish = [&]() { tmem_st_wait(); tc_fence_before(); group_sync(); };
 
     const int s_loc = gt / n;
@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) gcn_layer_tma_kernel(
         st_split<32>(tl + 64, tl + 96, x);
         publish();
         if (issuer) {
-            if (lane == 0) {
+            if (elect_one()) {
                 tc_fence_after();
                 if (sim) issue_gemm<4>(tg, tg + 64, tg + 96, tw_s, tw_s + 8192, umma_idesc(128, 64), 0);
                 else issue_gemm<4>(tg + 32, tg + 64, tg + 96, tw_s, tw_s + 8192, umma_idesc(128, 32), 0);

@@ -38,6 +38,17 @@ __device__ __forceinline__ void xf_store_row(uint32_t rp, const float (&v)[32]) 
     for (int c = 0; c < 8; ++c) sts128s(rp + c * 16, make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
 }
 
+// ---- optional phase trace (tools/trace_tc.cu builds this file with -DRGL_TC_TRACE): cycles between the marks below, summed
+// over every tile of group 0 of every CTA by a non-issuing thread (lane 0 of the group's second warp) ----
+#ifdef RGL_TC_TRACE
+__device__ unsigned long long g_tc_trace[32];
+#define TC_MARK(k) do { if (grp == 0 && gt == 32) { const long long t_ = clock64(); atomicAdd(&g_tc_trace[k], (unsigned long long)(t_ - tprev)); tprev = t_; } } while (0)
+void tc_trace_read(unsigned long long* out) { cudaMemcpyFromSymbol(out, g_tc_trace, sizeof(g_tc_trace)); }
+void tc_trace_reset() { unsigned long long z[32] = {}; cudaMemcpyToSymbol(g_tc_trace, z, sizeof(z)); }
+#else
+#define TC_MARK(k) do { } while (0)
+#endif
+
 // --------------------------------------------------------------------------------------------------- kernel
 constexpr int TC_COLS = 128;          // TMEM columns per group: [0,64) accumulators, [64,96) A hi, [96,128) A lo
 constexpr int C_D = 0, C_AHI = 64, C_ALO = 96;
@@ -63,38 +74,6 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tc_kern
     const int grp = warp >> 2, wq = warp & 3;
     const bool skip = a.flags & RGL_FLAG_SKIP, layerwise = a.flags & RGL_FLAG_LAYERWISE;
 
-    if (warp == 0) tmem_alloc(tslot, TC_COLS * G);
-    if (tid == 0) {
-        for (int i = 0; i < 2 + G; ++i) mbar_init(bars + i, 1);
-        fence_mbar_init();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    if (tid == 0) {
-        // stage 0: layer-1 embedding tiles (the first MMA needs only these); stage 1: everything else
-        const float* src = a.gw + graph_tc_off(a.L);
-        mbar_arrive_expect_tx(bars + 0, T_W1 * 4u);
-        bulk_g2s(tw, src, T_W1 * 4u, bars + 0);
-        const uint32_t rest = (uint32_t)(twf - T_W1) * 4u;
-        mbar_arrive_expect_tx(bars + 1, rest + (a.mw ? TMOTION_FLOATS * 4u : 0u));
-        bulk_g2s(tw + T_W1, src + T_W1, rest, bars + 1);
-        if (a.mw) bulk_g2s(tm, a.mw + MOTION_TC_OFF, TMOTION_FLOATS * 4u, bars + 1);
-    }
-
-    const uint32_t tbase = __shfl_sync(0xffffffffu, *tslot, 0);
-    const uint32_t tg = tbase + grp * TC_COLS;                        // this group's TMEM columns (lane field 0: MMA view)
-    const uint32_t tl = tg + ((uint32_t)(wq * 32) << 16);             // this warp's lane quadrant (ld / st view)
-    const uint32_t xf_s = __shfl_sync(0xffffffffu, smem_u32(xf_all), 0) + grp * XF_GROUP;
-    uint64_t* gbar = bars + 2 + grp;
-    uint32_t par = 0;
-    const uint32_t tw_s = __shfl_sync(0xffffffffu, smem_u32(tw), 0), tm_s = __shfl_sync(0xffffffffu, smem_u32(tm), 0);   // warp-uniform for the compiler
-    const bool issuer = wq == 0;                                      // warp-uniform; lane 0 of that warp issues the MMAs
-    auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" :: "r"(grp + 1) : "memory"); };
-    auto mma_wait = [&]() { mbar_wait(gbar, par); par ^= 1; tc_fence_after(); };
-    // A operand written -> visible to the MMAs issued after the barrier
-    auto publish = [&]() { tmem_st_wait(); tc_fence_before(); group_sync(); };
-
     // row identity inside a tile (the same for every tile)
     const bool is_robot = gt < SPT;
     const int hrow = gt - SPT;
@@ -103,8 +82,6 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tc_kern
     const bool row_used = gt < SPT * n;
     const int node = is_robot ? 0 : hum + 1;
     const int hbase = SPT + s_loc * Nh;                               // first human row of this thread's state
-    const uint32_t my_row = row_ptr(xf_s, gt);
-    const bool robot_warps = wq * 32 < SPT;                           // warp-uniform: this warp holds at least one robot row
 
     const int ntiles = a.ntiles;
     const int tstride = gridDim.x * G;
@@ -136,13 +113,56 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tc_kern
         }
     };
     int tile = blockIdx.x * G + grp;
+    load_raw(tile);                          // the first tile's raw rows: in flight under the prologue (TMEM allocation, weight TMA)
+
+    if (warp == 0) tmem_alloc(tslot, TC_COLS * G);
+    if (tid == 0) {
+        for (int i = 0; i < 2 + G; ++i) mbar_init(bars + i, 1);
+        fence_mbar_init();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0) {
+        // stage 0: layer-1 embedding tiles (the first MMA needs only these); stage 1: everything else
+        const float* src = a.gw + graph_tc_off(a.L);
+        mbar_arrive_expect_tx(bars + 0, T_W1 * 4u);
+        bulk_g2s(tw, src, T_W1 * 4u, bars + 0);
+        const uint32_t rest = (uint32_t)(twf - T_W1) * 4u;
+        mbar_arrive_expect_tx(bars + 1, rest + (a.mw ? TMOTION_FLOATS * 4u : 0u));
+        bulk_g2s(tw + T_W1, src + T_W1, rest, bars + 1);
+        if (a.mw) bulk_g2s(tm, a.mw + MOTION_TC_OFF, TMOTION_FLOATS * 4u, bars + 1);
+    }
+
+    const uint32_t tbase = __shfl_sync(0xffffffffu, *tslot, 0);
+    const uint32_t tg = tbase + grp * TC_COLS;                        // this group's TMEM columns (lane field 0: MMA view)
+    const uint32_t tl = tg + ((uint32_t)(wq * 32) << 16);             // this warp's lane quadrant (ld / st view)
+    const uint32_t xf_s = __shfl_sync(0xffffffffu, smem_u32(xf_all), 0) + grp * XF_GROUP;
+    uint64_t* gbar = bars + 2 + grp;
+    uint32_t par = 0;
+    const uint32_t tw_s = __shfl_sync(0xffffffffu, smem_u32(tw), 0), tm_s = __shfl_sync(0xffffffffu, smem_u32(tm), 0);   // warp-uniform for the compiler
+    const bool issuer = wq == 0;                                      // warp-uniform; lane 0 of that warp issues the MMAs
+#ifdef RGL_TC_TRACE
+    long long tprev = clock64();
+#endif
+    // (trace slots 20-23: time spent BEFORE the waits = the thread work; slots 0-14: the waits themselves)
+    auto group_sync = [&]() { TC_MARK(22); asm volatile("bar.sync %0, 128;" :: "r"(grp + 1) : "memory"); };
+    auto mma_wait = [&]() { TC_MARK(21); mbar_wait_sleepy(gbar, par); par ^= 1; tc_fence_after(); };
+    // A operand written -> visible to the MMAs issued after the barrier
+    auto publish = [&]() { TC_MARK(20); tmem_st_wait(); TC_MARK(23); tc_fence_before(); group_sync(); };
+
+    const uint32_t my_row = row_ptr(xf_s, gt);
+    const bool robot_warps = wq * 32 < SPT;                           // warp-uniform: this warp holds at least one robot row
     bool first = true;
 
     for (; tile < ntiles; tile += tstride) {
         const long s0 = (long)tile * SPT;
         const int cnt = (int)min((long)SPT, (long)a.B - s0);
         const bool valid = row_used && s_loc < cnt;
-        load_raw(tile);
+#ifdef RGL_TC_TRACE
+        tprev = clock64();
+        if (grp == 0 && gt == 32) atomicAdd(&g_tc_trace[31], 1ull);
+#endif
 
         // ================= embedding layer 1: hidden = relu([x_r | x_h | 1_r | 1_h] . W0cat^T), K = 16, N = 64 =================
         {
@@ -156,8 +176,9 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tc_kern
             st_split<16>(tl + C_AHI, tl + C_ALO, a0);
         }
         publish();
+        TC_MARK(0);   // after: publish()
         if (issuer) {
-            if (lane == 0) {
+            if (elect_one()) {
                 if (first) mbar_wait(bars + 0, 0);
                 tc_fence_after();
                 issue_gemm<2>(tg + C_D, tg + C_AHI, tg + C_ALO, tw_s + T_W0 * 4, tw_s + T_W0 * 4 + 64, umma_idesc(128, 64), 0);
@@ -167,6 +188,7 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tc_kern
         }
         prefetch_raw(tile + tstride);
         mma_wait();
+        TC_MARK(1);   // after: mma_wait()
 
         // ================= embedding layer 2: [X_h | X_r] = hidden . [W1_h ; W1_r]^T, K = 64 in two halves, N = 64 =================
         float x[32];
@@ -178,8 +200,9 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tc_kern
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(__uint_as_float(h0[j]), 0.f);
             st_split<32>(tl + C_AHI, tl + C_ALO, v);
             publish();
+            TC_MARK(2);   // after: publish()
             if (issuer) {
-                if (lane == 0) {
+                if (elect_one()) {
                     if (first) mbar_wait(bars + 1, 0);
                     tc_fence_after();
                     issue_gemm<4>(tg + C_D, tg + C_AHI, tg + C_ALO, tw_s + T_W1 * 4, tw_s + (T_W1 + 4096) * 4, umma_idesc(128, 64), 0);
@@ -190,10 +213,12 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tc_kern
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(__uint_as_float(h1[j]), 0.f);
             mma_wait();                      // first half consumed: its A columns may be overwritten
+            TC_MARK(3);   // after: mma_wait()
             st_split<32>(tl + C_AHI, tl + C_ALO, v);
             publish();
+            TC_MARK(4);   // after: publish()
             if (issuer) {
-                if (lane == 0) {
+                if (elect_one()) {
                     tc_fence_after();
                     issue_gemm<4>(tg + C_D, tg + C_AHI, tg + C_ALO, tw_s + (T_W1 + 2048) * 4, tw_s + (T_W1 + 4096 + 2048) * 4, umma_idesc(128, 64), 1);
                     umma_commit(gbar);
@@ -202,6 +227,7 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tc_kern
             }
             if (first) { mbar_wait(bars + 1, 0); first = false; }      // the biases arrive with stage 1
             mma_wait();
+            TC_MARK(5);   // after: mma_wait()
             tmem_ld64(tl + C_D, h0, h1);     // h0 = human-weight version, h1 = robot-weight version
             const float* bias = tw + tc_bias_off(a.L) + (is_robot ? 32 : 0);
 #pragma unroll
@@ -226,8 +252,9 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tc_kern
 
             st_split<32>(tl + C_AHI, tl + C_ALO, x);
             publish();       // also: feature rows in xf visible; every read of the previous layer's H W rows is done
+            TC_MARK(6);   // after: publish()
             if (issuer) {
-                if (lane == 0) {
+                if (elect_one()) {
                     tc_fence_after();
                     if (l == 0) {
                         // one N = 64 MMA chain: columns [0,32) = Y = X w_a, columns [32,64) = X Ws[0]
@@ -243,6 +270,7 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tc_kern
                 __syncwarp();
             }
             mma_wait();
+            TC_MARK(7);   // after: mma_wait()
 
             if (sim) {
                 // ---- this row's similarity logits against the state's feature rows + softmax (FMA pipe) ----
@@ -284,6 +312,7 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tc_kern
                     }
                 }
                 group_sync();                                // every read of the feature rows is done
+                TC_MARK(8);   // after: group_sync()
             }
 
             // ---- H W rows -> xf; H' = relu(sum_j A[i][j] (H W)[j]) (+ H) ----
@@ -297,6 +326,7 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tc_kern
             }
             tc_fence_before();
             group_sync();
+            TC_MARK(9);   // after: group_sync()
             if (active && row_used) {
                 float acc[32];
 #pragma unroll
@@ -325,6 +355,7 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tc_kern
             }
             if (!last && layerwise) {                        // the next layer's similarity needs the new feature rows
                 group_sync();
+                TC_MARK(10);   // after: group_sync()
                 xf_store_row(my_row, x);
             }
         }
@@ -340,8 +371,9 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tc_kern
             // cores (N = 64), the 64 -> 5 output layer per thread on the FMA pipe
             st_split<32>(tl + C_AHI, tl + C_ALO, x);
             publish();
+            TC_MARK(11);   // after: publish()
             if (issuer) {
-                if (lane == 0) {
+                if (elect_one()) {
                     tc_fence_after();
                     issue_gemm<4>(tg + C_D, tg + C_AHI, tg + C_ALO, tm_s + TM_W0 * 4, tm_s + (TM_W0 + 2048) * 4, umma_idesc(128, 64), 0);
                     umma_commit(gbar);
@@ -349,6 +381,7 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tc_kern
                 __syncwarp();
             }
             mma_wait();
+            TC_MARK(12);   // after: mma_wait()
             uint32_t h0[32], h1[32];
             tmem_ld64(tl + C_D, h0, h1);
             float part[HD];
@@ -378,8 +411,10 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tc_kern
             // stage the final rows in xf, then copy out in HBM order: 512 contiguous bytes per warp instruction
             // (measured faster than each thread streaming its own 128-byte row: 924 vs 854 M states/s at B = 1 M)
             group_sync();                                    // every read of the last H W rows is done
+            TC_MARK(13);   // after: group_sync()
             xf_store_row(my_row, x);
             group_sync();
+            TC_MARK(14);   // after: group_sync()
             float* dst = a.H + s0 * n * XD;
             const int chunks = cnt * n * 8;
             for (int idx = gt; idx < chunks; idx += 128) {
@@ -390,6 +425,7 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tc_kern
             }
             // the next tile writes xf only after further group barriers: no extra barrier needed here
         }
+        load_raw(tile + tstride);            // next tile's raw rows (prefetched into L2 above): consumed at the top of the loop
     }
 
     // teardown: the bulk copies must have landed before the CTA's shared memory is released

@@ -85,6 +85,14 @@ __device__ __forceinline__ void st_split(uint32_t t_hi, uint32_t t_lo, const flo
     }
 }
 
+// one lane of a converged warp, chosen by the hardware (elect.sync): the compiler knows a single thread runs the guarded code,
+// so the uniform-datapath tcgen05.mma is predicated directly instead of being wrapped in a divergence loop
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // one elected thread: D[128 x N] (+)= A * W^T over KS k-steps of 8, 3xTF32 (small terms first).  Every operand is
 // warp-uniform (derived from __shfl_sync(.., 0) values), so each MMA is one UTCHMMA with uniform-register operands.
 template <int KS>

@@ -69,8 +69,8 @@ __global__ void __launch_bounds__(128 * G, 1) value_head_tc_kernel(const float* 
     uint32_t par0 = 0, par1 = 0;
     const bool issuer = wq == 0;
     auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" :: "r"(grp + 1) : "memory"); };
-    auto mma_wait0 = [&]() { mbar_wait(gbar0, par0); par0 ^= 1; tc_fence_after(); };
-    auto mma_wait1 = [&]() { mbar_wait(gbar1, par1); par1 ^= 1; tc_fence_after(); };
+    auto mma_wait0 = [&]() { mbar_wait_sleepy(gbar0, par0); par0 ^= 1; tc_fence_after(); };
+    auto mma_wait1 = [&]() { mbar_wait_sleepy(gbar1, par1); par1 ^= 1; tc_fence_after(); };
     auto publish = [&]() { tmem_st_wait(); tc_fence_before(); group_sync(); };
     const float* bias = tw + TV_BIAS;
     constexpr uint32_t W2A = TV_NP * 32 * 4;            // bytes per layer-2 k atom
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(128 * G, 1) value_head_tc_kernel(const float* 
         }
         publish();
         if (issuer) {
-            if (lane == 0) {
+            if (elect_one()) {
                 if (first) mbar_wait(bars + 0, 0);
                 tc_fence_after();
                 issue_gemm<4>(tg + VC_D, tg + VC_A0, tg + VC_A0 + 32, tw_s + TV_W0 * 4, tw_s + (TV_W0 + 1024) * 4, umma_idesc(128, 32), 0);
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(128 * G, 1) value_head_tc_kernel(const float* 
         }
         publish();
         if (issuer) {
-            if (lane == 0) {
+            if (elect_one()) {
                 if (first) mbar_wait(bars + 1, 0);
                 tc_fence_after();
                 issue_gemm<4>(tg + VC_D, tg + VC_A1, tg + VC_A1 + 32, tw_s + TV_W1 * 4, tw_s + (TV_W1 + TV_NP * 32) * 4, umma_idesc(128, TV_NP), 0);
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(128 * G, 1) value_head_tc_kernel(const float* 
             }
             publish();
             if (issuer) {
-                if (lane == 0) {
+                if (elect_one()) {
                     if (first && q == 0) mbar_wait(bars + 2, 0);
                     tc_fence_after();
                     if (q < 3) issue_gemm<4>(tg + VC_D, tg + acol, tg + acol + 32, w2 + q * W2A, w2 + (4 + q) * W2A, umma_idesc(128, TV_NP), q > 0);
