@@ -369,7 +369,12 @@ __global__ void __launch_bounds__(128) rate_probe(long long* cycles, int rounds)
 }
 // Same measurement with warp-uniform operands (no divergence "waterfall" around UTCHMMA): one warp issues (lane 0),
 // optionally HAMMER other warps stream LDS.128 from shared memory at the same time (contention for the B-operand fetch).
-template <int N, bool TS, int HAMMER>
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+template <int N, bool TS, int HAMMER, bool ELECT = false>
 __global__ void __launch_bounds__(32 * (1 + HAMMER)) rate2_probe(long long* cycles, float* sink, int rounds) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint64_t bar;
@@ -393,7 +398,7 @@ __global__ void __launch_bounds__(32 * (1 + HAMMER)) rate2_probe(long long* cycl
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) {
+        if (ELECT ? elect_one() : (lane == 0)) {
             tc_fence_after();
             constexpr uint32_t idesc = make_idesc(128, N);
             const long long t0 = clock64();
@@ -492,17 +497,17 @@ static void run_rate3() {
     }
 }
 
-template <int N, bool TS, int HAMMER>
+template <int N, bool TS, int HAMMER, bool ELECT = false>
 static void run_rate2() {
     long long* cyc; float* sink; CK(cudaMalloc(&cyc, 16)); CK(cudaMalloc(&sink, 4096 * 4));
     const size_t smem = 1024 + 32768 + N * 128;
-    CK(cudaFuncSetAttribute(rate2_probe<N, TS, HAMMER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(rate2_probe<N, TS, HAMMER, ELECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int rounds : {1, 8, 64}) {
-        rate2_probe<N, TS, HAMMER><<<1, 32 * (1 + HAMMER), smem>>>(cyc, sink, rounds);
+        rate2_probe<N, TS, HAMMER, ELECT><<<1, 32 * (1 + HAMMER), smem>>>(cyc, sink, rounds);
         CK(cudaGetLastError());
         CK(cudaDeviceSynchronize());
         long long c[2]; CK(cudaMemcpy(c, cyc, 16, cudaMemcpyDeviceToHost));
-        printf("rate2 %s N=%d hammer-warps=%d: %d MMAs: issue %lld cycles, issue+complete %lld cycles -> %.1f cycles per MMA\n", TS ? "TS" : "SS", N, HAMMER,
+        printf("rate2 %s%s N=%d hammer-warps=%d: %d MMAs: issue %lld cycles, issue+complete %lld cycles -> %.1f cycles per MMA\n", TS ? "TS" : "SS", ELECT ? " elect.sync" : " lane0", N, HAMMER,
                rounds * 12, c[0], c[1], (double)c[1] / (rounds * 12));
     }
 }
@@ -534,6 +539,7 @@ int main(int argc, char** argv) {
         case 9: run_rate2<32, true, 0>(); run_rate2<64, true, 0>(); run_rate2<32, false, 0>(); run_rate2<64, false, 0>();
                 run_rate2<64, true, 8>(); run_rate2<64, true, 15>(); run_rate2<32, true, 15>(); return 0;
         case 10: run_rate3<64, 1>(); run_rate3<64, 2>(); run_rate3<64, 4>(); run_rate3<32, 4>(); run_rate3<128, 1>(); run_rate3<256, 1>(); return 0;
+        case 11: run_rate2<32, true, 0, true>(); run_rate2<64, true, 0, true>(); run_rate2<32, true, 0, false>(); run_rate2<128, true, 0, true>(); return 0;
         case 6: return run_gemm<32, 64, 1>("3xTF32 SS K=32 N=64");
         case 7: return run_gemm<64, 32, 1>("3xTF32 SS K=64 N=32");
     }
