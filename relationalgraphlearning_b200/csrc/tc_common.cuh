@@ -77,8 +77,13 @@ __device__ __forceinline__ void st_split(uint32_t t_hi, uint32_t t_lo, const flo
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
+#ifdef RGL_SPLIT_TRUNC      // experiment only: 2 instead of 3 instructions per element, +3 % throughput, 1.7x the error (H 5.2e-5 vs 3.1e-5 at scale 20)
+            hi[j] = __float_as_uint(v[b + j]);                                             // the tensor core drops the low 13 bits
+            lo[j] = __float_as_uint(v[b + j] - __uint_as_float(hi[j] & 0xffffe000u));
+#else
             hi[j] = (__float_as_uint(v[b + j]) + 0x1000u) & 0xffffe000u;
             lo[j] = __float_as_uint(v[b + j] - __uint_as_float(hi[j]));
+#endif
         }
         tmem_st16(t_hi + b, hi);
         tmem_st16(t_lo + b, lo);
