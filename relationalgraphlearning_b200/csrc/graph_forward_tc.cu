@@ -283,15 +283,17 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tc_kern
                     for (int j = 0; j < NMAX; ++j) {
                         if (N > 0 || j < n) {
                             const uint32_t rp = row_ptr(xf_s, j == 0 ? s_loc : hbase + j - 1);
-                            float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+                            f32x2 d01 = 0ull, d23 = 0ull;           // four partial sums, two per packed FFMA2
 #pragma unroll
                             for (int c = 0; c < 8; ++c) {
-                                const float4 xv = lds128s(rp + c * 16);
-                                d0 = fmaf(__uint_as_float(yr[4 * c + 0]), xv.x, d0);
-                                d1 = fmaf(__uint_as_float(yr[4 * c + 1]), xv.y, d1);
-                                d2 = fmaf(__uint_as_float(yr[4 * c + 2]), xv.z, d2);
-                                d3 = fmaf(__uint_as_float(yr[4 * c + 3]), xv.w, d3);
+                                f32x2 xlo, xhi;
+                                lds128s2(rp + c * 16, xlo, xhi);
+                                fma2(d01, pack2u(yr[4 * c + 0], yr[4 * c + 1]), xlo);
+                                fma2(d23, pack2u(yr[4 * c + 2], yr[4 * c + 3]), xhi);
                             }
+                            float d0, d1, d2, d3;
+                            unpack2(d01, d0, d1);
+                            unpack2(d23, d2, d3);
                             p[j] = (d0 + d1) + (d2 + d3);
                             mx = fmaxf(mx, p[j]);
                         }
@@ -328,23 +330,26 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tc_kern
             group_sync();
             TC_MARK(9);   // after: group_sync()
             if (active && row_used) {
-                float acc[32];
+                f32x2 acc2[16];
 #pragma unroll
-                for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+                for (int c = 0; c < 16; ++c) acc2[c] = 0ull;
 #pragma unroll
                 for (int j = 0; j < NMAX; ++j) {
                     if (N > 0 || j < n) {
                         const uint32_t rp = row_ptr(xf_s, j == 0 ? s_loc : hbase + j - 1);
+                        const f32x2 pj = pack2(p[j], p[j]);
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
-                            const float4 hv = lds128s(rp + c * 16);
-                            acc[4 * c + 0] = fmaf(p[j], hv.x, acc[4 * c + 0]);
-                            acc[4 * c + 1] = fmaf(p[j], hv.y, acc[4 * c + 1]);
-                            acc[4 * c + 2] = fmaf(p[j], hv.z, acc[4 * c + 2]);
-                            acc[4 * c + 3] = fmaf(p[j], hv.w, acc[4 * c + 3]);
+                            f32x2 hlo, hhi;
+                            lds128s2(rp + c * 16, hlo, hhi);
+                            fma2(acc2[2 * c], pj, hlo);
+                            fma2(acc2[2 * c + 1], pj, hhi);
                         }
                     }
                 }
+                float acc[32];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) unpack2(acc2[c], acc[2 * c], acc[2 * c + 1]);
                 if (skip) {
 #pragma unroll
                     for (int c = 0; c < 32; ++c) x[c] += fmaxf(acc[c], 0.f);

@@ -112,6 +112,17 @@ __device__ __forceinline__ void issue_gemm(uint32_t d, uint32_t a_hi, uint32_t a
     }
 }
 
+// ---- packed fp32x2 arithmetic (sm_100: FFMA2 = two IEEE fp32 FMAs in one instruction, same results as two fmaf) ----
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ f32x2 pack2u(uint32_t a, uint32_t b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ void fma2(f32x2& d, f32x2 a, f32x2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b)); }
+// 16 bytes of shared memory as two fp32 pairs
+__device__ __forceinline__ void lds128s2(uint32_t saddr, f32x2& lo, f32x2& hi) {
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "r"(saddr));
+}
+
 // shared memory through 32-bit addresses (one LOP3 per swizzled access instead of 64-bit generic pointer arithmetic)
 __device__ __forceinline__ float4 lds128s(uint32_t saddr) {
     float4 v;
