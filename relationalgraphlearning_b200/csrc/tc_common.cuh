@@ -67,6 +67,18 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// ---- packed fp32x2 arithmetic (sm_100: FFMA2 = two IEEE fp32 FMAs in one instruction, same results as two fmaf) ----
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ f32x2 pack2u(uint32_t a, uint32_t b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ void fma2(f32x2& d, f32x2 a, f32x2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b)); }
+// 16 bytes of shared memory as two fp32 pairs
+__device__ __forceinline__ void lds128s2(uint32_t saddr, f32x2& lo, f32x2& hi) {
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "r"(saddr));
+}
+
 // A-operand row: 16 / 32 values -> tf32 hi / lo columns of this thread's TMEM lane.  hi = x rounded to nearest tf32
 // (integer add of half an ulp, then mask: cvt.rna.tf32 is emulated with 3 instructions on sm_100), lo = x - hi exactly;
 // the tensor core drops the low 13 bits of lo (2^-23 relative to x).
@@ -82,7 +94,12 @@ __device__ __forceinline__ void st_split(uint32_t t_hi, uint32_t t_lo, const flo
             lo[j] = __float_as_uint(v[b + j] - __uint_as_float(hi[j] & 0xffffe000u));
 #else
             hi[j] = (__float_as_uint(v[b + j]) + 0x1000u) & 0xffffe000u;
-            lo[j] = __float_as_uint(v[b + j] - __uint_as_float(hi[j]));
+            if (j & 1) {                                   // lo = x - hi for two elements with one packed subtract
+                float l0, l1;
+                unpack2(sub2(pack2(v[b + j - 1], v[b + j]), pack2u(hi[j - 1], hi[j])), l0, l1);
+                lo[j - 1] = __float_as_uint(l0);
+                lo[j] = __float_as_uint(l1);
+            }
 #endif
         }
         tmem_st16(t_hi + b, hi);
@@ -110,17 +127,6 @@ __device__ __forceinline__ void issue_gemm(uint32_t d, uint32_t a_hi, uint32_t a
         umma_tf32_ts(d, a_hi + ks * 8, bh, idesc, 1);
         acc = 1;
     }
-}
-
-// ---- packed fp32x2 arithmetic (sm_100: FFMA2 = two IEEE fp32 FMAs in one instruction, same results as two fmaf) ----
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pack2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
-__device__ __forceinline__ f32x2 pack2u(uint32_t a, uint32_t b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b)); return r; }
-__device__ __forceinline__ void unpack2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-__device__ __forceinline__ void fma2(f32x2& d, f32x2 a, f32x2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b)); }
-// 16 bytes of shared memory as two fp32 pairs
-__device__ __forceinline__ void lds128s2(uint32_t saddr, f32x2& lo, f32x2& hi) {
-    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "r"(saddr));
 }
 
 // shared memory through 32-bit addresses (one LOP3 per swizzled access instead of 64-bit generic pointer arithmetic)
