@@ -5,7 +5,7 @@
 //
 //   group   = 128 threads = one UMMA M-tile of 128 graph-node rows = SPT = 128 / n whole states.  A thread owns ONE node
 //             row end to end (TMEM lane = row, tcgen05.ld/st 32x32b: thread t <-> lane t).  Groups are independent
-//             pipelines (own mbarrier, own named barrier, own 128 TMEM columns, own 16 KB feature buffer) that only
+//             pipelines (own mbarrier, own named barrier, own 128 TMEM columns, own 18 KB feature buffer) that only
 //             share the weight tiles of their CTA: while one group waits for its MMAs the others compute.
 //   rows    = robot-first inside a tile: rows [0,SPT) are the robots of the SPT states, rows SPT + s*Nh + j the humans,
 //             so only the first warp holds robot rows (value path: the last layer runs for that warp only).
@@ -19,8 +19,12 @@
 //             features and two indicator columns that carry the biases; a row has zeros in the other agent type's
 //             slots) and layer 2 stacks them along n (N=64: columns 0-31 human weights, 32-63 robot weights; each row
 //             keeps the half that belongs to it).
-//   per-state work (similarity row, softmax, A.H) stays on the FMA pipe, one node row per thread, neighbours' feature
-//             rows read from the group's swizzled shared-memory buffer; attention weights never leave registers.
+//             Y = H w_a and H W_0 share their A operand (one N=64 chain over the stacked tile [w_a^T ; Ws[0]^T]) and the
+//             GCN layer is evaluated as relu(A (H W)) -- the reference's (A H) W reassociated.  The MMAs are issued by the
+//             elect.sync lane of the group's first warp (a plain `lane == 0` guard makes the compiler wrap every
+//             UTCHMMA in a divergence loop: 45 instead of 16-32 cycles per MMA).
+//   per-state work (similarity row, softmax, A.(HW)) stays on the FMA pipe (packed FFMA2), one node row per thread,
+//             neighbours' rows read from the group's padded shared-memory buffer; attention weights never leave registers.
 #include <stdlib.h>
 #include "kernels.h"
 #include "tc_common.cuh"
