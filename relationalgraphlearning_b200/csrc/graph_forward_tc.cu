@@ -393,22 +393,30 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tc_kern
             TC_MARK(12);   // after: mma_wait()
             uint32_t h0[32], h1[32];
             tmem_ld64(tl + C_D, h0, h1);
-            float part[HD];
+            f32x2 part2[HD];                         // two partial sums per output (packed FFMA2)
 #pragma unroll
-            for (int c = 0; c < HD; ++c) part[c] = tm[TM_B1 + c];
+            for (int c = 0; c < HD; ++c) part2[c] = 0ull;
 #pragma unroll
             for (int k4 = 0; k4 < 16; ++k4) {
                 const float4 b = lds128(tm + TM_B0 + 4 * k4);
                 const uint32_t* hh = k4 < 8 ? h0 : h1;
                 const int o = (k4 & 7) * 4;
-                const float v0 = fmaxf(__uint_as_float(hh[o + 0]) + b.x, 0.f), v1 = fmaxf(__uint_as_float(hh[o + 1]) + b.y, 0.f);
-                const float v2 = fmaxf(__uint_as_float(hh[o + 2]) + b.z, 0.f), v3 = fmaxf(__uint_as_float(hh[o + 3]) + b.w, 0.f);
+                const f32x2 v01 = pack2(fmaxf(__uint_as_float(hh[o + 0]) + b.x, 0.f), fmaxf(__uint_as_float(hh[o + 1]) + b.y, 0.f));
+                const f32x2 v23 = pack2(fmaxf(__uint_as_float(hh[o + 2]) + b.z, 0.f), fmaxf(__uint_as_float(hh[o + 3]) + b.w, 0.f));
 #pragma unroll
                 for (int c = 0; c < HD; ++c) {
-                    const float4 w = lds128(tm + TM_W1 + c * MH + 4 * k4);
-                    part[c] = fmaf(v0, w.x, part[c]); part[c] = fmaf(v1, w.y, part[c]);
-                    part[c] = fmaf(v2, w.z, part[c]); part[c] = fmaf(v3, w.w, part[c]);
+                    f32x2 wlo, whi;
+                    lds128s2(tm_s + (TM_W1 + c * MH + 4 * k4) * 4, wlo, whi);
+                    fma2(part2[c], v01, wlo);
+                    fma2(part2[c], v23, whi);
                 }
+            }
+            float part[HD];
+#pragma unroll
+            for (int c = 0; c < HD; ++c) {
+                float lo_, hi_;
+                unpack2(part2[c], lo_, hi_);
+                part[c] = (lo_ + hi_) + tm[TM_B1 + c];
             }
             if (!is_robot && valid) {
                 float* so = a.S + ((s0 + s_loc) * Nh + hum) * HD;
