@@ -180,12 +180,7 @@ static cudaError_t launch_gcn(const float* X, const float* A, const float* W, co
                               float* Hout, float* Aout, int num_sms, size_t max_smem, cudaStream_t st) {
     const size_t smem = gcn_smem_bytes(TS, n);
     if (smem > max_smem) return cudaErrorInvalidConfiguration;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gcn_layer_kernel<TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    if (cudaError_t e = ensure_dyn_smem(gcn_layer_kernel<TS>, (int)max_smem)) return e;
     const int ntiles = (B + TS - 1) / TS;
     int nwarps = TS == 32 ? n : n * TS / 16;            // one warp per 32-row (TS = 32) / 16-row block
     const int cap = TS == 32 ? 6 : 12;

@@ -478,12 +478,7 @@ static cudaError_t launch_gl_tma(const float* X, const float* A, const float* W,
     const int spt = 128 / n;
     CUtensorMap mx, mh;
     if (!make_row_map(&mx, X, (long)B * n, spt * n) || !make_row_map(&mh, Hout, (long)B * n, spt * n)) return cudaErrorNotSupported;
-    static bool attr_set = false;     // benign race: idempotent
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gcn_layer_tma_kernel<N, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    if (cudaError_t e = ensure_dyn_smem(gcn_layer_tma_kernel<N, G>, (int)max_smem)) return e;
     const int ntiles = (B + spt - 1) / spt;
     int per_sm = (int)((228 * 1024) / (smem + 1024));
     const int max_cta = G <= 2 ? 2 : 1;
@@ -500,12 +495,7 @@ static cudaError_t launch_gl(const float* X, const float* A, const float* W, con
                              float* Aout, int num_sms, size_t max_smem, cudaStream_t st) {
     const size_t smem = 1024 + (4096 + (size_t)G * 4096) * 4 + G * 8 + 16;
     if (smem > max_smem) return cudaErrorInvalidConfiguration;
-    static bool attr_set = false;     // benign race: idempotent
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gcn_layer_tc_kernel<N, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    if (cudaError_t e = ensure_dyn_smem(gcn_layer_tc_kernel<N, G>, (int)max_smem)) return e;
     const int spt = 128 / n;
     const int ntiles = (B + spt - 1) / spt;
     const int per_sm = G <= 2 ? 2 : 1;                   // 512 TMEM columns per SM = four 128-column groups

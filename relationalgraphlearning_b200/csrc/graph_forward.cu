@@ -688,12 +688,7 @@ static cudaError_t launch_graph(const GraphArgs& a, int num_sms, size_t max_smem
     const int nrb = n * TS / (8 * RT);
     const int cap = RPT > 0 ? n : (N == 6 ? 12 : 16);
     const int nwarps = nrb < cap ? nrb : cap;
-    static bool attr_set = false;     // benign race: idempotent
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(graph_forward_kernel<TS, RT, N, RPT, MMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    if (cudaError_t e = ensure_dyn_smem(graph_forward_kernel<TS, RT, N, RPT, MMA>, (int)max_smem)) return e;
     int per_sm = (int)((228 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
     const int max_cta = (RPT > 0 && N <= 8) ? 2 : 1;          // matches the kernel's __launch_bounds__ (register budget)

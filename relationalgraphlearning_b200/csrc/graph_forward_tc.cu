@@ -465,12 +465,7 @@ static cudaError_t launch_tc(const GraphArgs& a, int num_sms, size_t max_smem, c
     GraphArgs b = a;
     const int spt = 128 / n;
     b.ntiles = (a.B + spt - 1) / spt;
-    static bool attr_set = false;     // benign race: idempotent
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(graph_forward_tc_kernel<N, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    if (cudaError_t e = ensure_dyn_smem(graph_forward_tc_kernel<N, G>, (int)max_smem)) return e;
     int per_sm = (int)((228 * 1024) / (smem + 1024));
     const int max_cta = G <= 2 ? 2 : 1;                       // matches __launch_bounds__ and the 512 TMEM columns of an SM
     if (per_sm > max_cta) per_sm = max_cta;

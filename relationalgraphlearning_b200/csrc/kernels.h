@@ -1,8 +1,32 @@
 // Internal launch interface between capi.cu and the kernel translation units.
 #pragma once
+#include <mutex>
 #include "common.cuh"
 
 namespace rgl {
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: set it once per (kernel, device).  A small table
+// keyed by the kernel's address (one table per translation unit), guarded by a mutex.
+static inline cudaError_t ensure_dyn_smem_ptr(const void* kernel, int bytes) {
+    struct Entry { const void* k; unsigned long long done; };
+    static Entry table[64];
+    static int count = 0;
+    static std::mutex mu;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    Entry* ent = nullptr;
+    for (int i = 0; i < count; ++i)
+        if (table[i].k == kernel) { ent = &table[i]; break; }
+    if (ent == nullptr && count < 64) { ent = &table[count++]; ent->k = kernel; ent->done = 0; }
+    if (ent != nullptr && dev < 64 && (ent->done >> dev & 1ull)) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess && ent != nullptr && dev < 64) ent->done |= 1ull << dev;
+    return e;
+}
+template <typename Kernel>
+static inline cudaError_t ensure_dyn_smem(Kernel kernel, int bytes) { return ensure_dyn_smem_ptr(reinterpret_cast<const void*>(kernel), bytes); }
 
 typedef RglGraphSave GraphSave;      // optional activation saves of the training forward (include/rgl_b200.h)
 

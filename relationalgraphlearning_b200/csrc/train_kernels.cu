@@ -324,12 +324,7 @@ cudaError_t run_linear_bwd(const RglRows* G, int N, const RglRows* mask, const R
     size_t smem = ((size_t)NP4 * (KP32 + 4) + (size_t)LT * (NP32 + 4) + (size_t)LT * (KP32 + 4)) * sizeof(float);
     if (dW && smem < 8 * 1024 * sizeof(float)) smem = 8 * 1024 * sizeof(float);      // row-split reduction scratch
     if (smem > max_smem) return cudaErrorInvalidConfiguration;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(rows_linear_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    if (cudaError_t e = ensure_dyn_smem(rows_linear_bwd_kernel, (int)max_smem)) return e;
     auto vec_ok = [](const Rows& r, int width) {
         return r.ptr != nullptr && (reinterpret_cast<uintptr_t>(r.ptr) & 15u) == 0 && (r.ld & 3) == 0 && (r.gstride & 3) == 0 && (width & 3) == 0;
     };

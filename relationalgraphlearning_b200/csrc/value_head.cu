@@ -169,13 +169,8 @@ size_t value_smem_bytes() { return (4 + VALUE_FLOATS + 2 * VT * LDX + 2 * VT * L
 
 cudaError_t run_value_head(const float* E, int B, const float* vw, float* V, float* v0, float* v1, float* v2, int use_tma, int num_sms,
                            cudaStream_t st) {
-    static bool attr_set = false;
     const size_t smem = value_smem_bytes();
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(value_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    if (cudaError_t e = ensure_dyn_smem(value_head_kernel, (int)smem)) return e;
     const int ntiles = (B + VT - 1) / VT;
     const int grid = ntiles < num_sms ? ntiles : num_sms;
     value_head_kernel<<<grid, 256, smem, st>>>(E, B, vw, V, v0, v1, v2, ntiles, use_tma);

@@ -224,12 +224,7 @@ template <int G>
 static cudaError_t launch_vtc(const float* E, int B, const float* vw, float* V, int num_sms, size_t max_smem, cudaStream_t st) {
     const size_t smem = 1024 + (size_t)TVALUE_FLOATS * 4 + (3 + 2 * G) * 8 + 16;
     if (smem > max_smem) return cudaErrorInvalidConfiguration;
-    static bool attr_set = false;     // benign race: idempotent
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(value_head_tc_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    if (cudaError_t e = ensure_dyn_smem(value_head_tc_kernel<G>, (int)max_smem)) return e;
     const int ntiles = (B + 127) / 128;
     const int want = (ntiles + G - 1) / G;
     const int grid = want < num_sms ? want : num_sms;
