@@ -172,8 +172,8 @@ def test_full_size_properties_c2(cuda_device):
         perm = torch.randperm(B, device=cuda_device)
         assert torch.equal(ve((robot[perm], humans[perm])), V[perm])
         assert torch.equal(g1((robot[perm], humans[perm])), H[perm])
-        # chunks of 1000 states take the small-batch kernel (fp32 FFMA GEMMs), the full batch the tensor-core variant
-        # (3xTF32): equal within the parity tolerance, bit-identical when the same variant is forced
+        # chunks run with other groups-per-CTA / tile boundaries than the full batch: equal within the parity tolerance
+        # (rows are independent, so in practice bit-identical); the fp32-FMA path agrees with the 3xTF32 path
         parts = [ve((robot[i:i + 1000], humans[i:i + 1000])) for i in range(0, B, 1000)]
         assert_close_scaled(torch.cat(parts), V, REL, 'V split')
         g1.fp32_fma = True
@@ -196,6 +196,43 @@ def test_full_size_properties_c2(cuda_device):
         assert_close_scaled(V[idx], O.value_forward(g['graph1'], g['value'], rc, hc), REL, 'V spot')
         assert_close_scaled(H[idx], O.rgl_forward(g['graph1'], rc, hc), REL, 'H spot')
         assert torch.isfinite(H).all() and torch.isfinite(S).all()
+
+
+
+@pytest.mark.parametrize('case,nh,B', [('fwd_nh10_s0', 10, 8192), ('fwd_nh20_s0', 20, 16384)])
+def test_full_size_properties_c4_c5_shapes(case, nh, B, cuda_device):
+    """BASELINE configs C4 / C5 shapes (Nh = 10, B = 8192; Nh = 20, B = 16384): size-independent properties + oracle spot checks."""
+    g = load_golden(case)
+    g1, ve, g2, sp = modules_from_golden(g, cuda_device)
+    robot, humans = synthetic_states(B, nh, seed=4321 + nh, device=cuda_device)
+    with torch.no_grad():
+        H, V, S = g1((robot, humans)), ve((robot, humans)), sp((robot, humans), None)[1]
+        assert torch.isfinite(H).all() and torch.isfinite(V).all() and torch.isfinite(S).all()
+        # states are independent: a batch permutation permutes the rows bit for bit
+        perm = torch.randperm(B, device=cuda_device)
+        assert torch.equal(ve((robot[perm], humans[perm])), V[perm])
+        assert torch.equal(g1((robot[perm], humans[perm])), H[perm])
+        # ragged split (tile boundaries move)
+        cut = B // 3 + 7
+        parts = torch.cat([g1((robot[:cut], humans[:cut])), g1((robot[cut:], humans[cut:]))])
+        assert_close_scaled(parts, H, REL, 'H split')
+        # the value head sees only the robot row; the E-only path (last layer for the robot rows only) matches the H path
+        assert torch.equal(g1.run(robot, humans, want_E=True)['E'], H[:, 0, :])
+        # humans_bcast: every state of a group of 4 reads the humans of the group's first state
+        hb = humans[::4].contiguous()
+        Vb = ve.run(robot, hb, humans_bcast=4)
+        Vm = ve((robot, hb.repeat_interleave(4, dim=0)))
+        assert torch.equal(Vb.view(-1), Vm.view(-1))
+        # permuting the humans permutes S and leaves V unchanged up to summation order
+        hp = torch.randperm(nh, device=cuda_device)
+        assert_close_scaled(sp((robot, humans[:, hp]), None)[1], S[:, hp], REL, 'S perm')
+        assert_close_scaled(ve((robot, humans[:, hp])), V, REL, 'V perm')
+        # oracle spot check on 64 states
+        idx = torch.arange(0, B, B // 64)
+        rc, hc = robot[idx].cpu(), humans[idx].cpu()
+        assert_close_scaled(V[idx], O.value_forward(g['graph1'], g['value'], rc, hc), REL, 'V spot')
+        assert_close_scaled(H[idx], O.rgl_forward(g['graph1'], rc, hc), REL, 'H spot')
+        assert_close_scaled(S[idx], O.statepred_forward(g['graph2'], g['motion'], rc, hc), REL, 'S spot')
 
 
 def test_weight_update_invalidates_packed_blob(cuda_device):
