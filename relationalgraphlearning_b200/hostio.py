@@ -26,7 +26,6 @@ class HostStream(object):
         self.robot_d = [torch.empty(batch, 1, 9, device=self.dev) for _ in range(depth)]
         self.humans_d = [torch.empty(batch, human_num, 5, device=self.dev) for _ in range(depth)]
         self.out_h = [torch.empty(self.out_shape).pin_memory() for _ in range(depth)]
-        self.done = [torch.cuda.Event() for _ in range(depth)]
         self.graphs = {}
         self.use_graphs = use_graphs
         self.count = 0
@@ -59,9 +58,9 @@ class HostStream(object):
                 self._sequence(k, robot_h, humans_h)
                 s.synchronize()
                 self._warm = True
-            pinned = self.use_graphs and robot_h.is_pinned() and humans_h.is_pinned()
             key = (k, robot_h.data_ptr(), humans_h.data_ptr())
-            g = self.graphs.get(key) if pinned else None
+            g = self.graphs.get(key) if self.use_graphs else None      # a cached graph implies the buffers were pinned at capture
+            pinned = g is not None or (self.use_graphs and robot_h.is_pinned() and humans_h.is_pinned())
             if g is None and pinned and len(self.graphs) < self.MAX_GRAPHS:
                 s.synchronize()
                 g = torch.cuda.CUDAGraph()
@@ -73,12 +72,12 @@ class HostStream(object):
             else:
                 out = self._sequence(k, robot_h, humans_h)
                 out.record_stream(s)
-            self.done[k].record(s)
         return k
 
     def result(self, slot):
-        """Blocks until the slot's result has landed in pinned host memory and returns that buffer."""
-        self.done[slot].synchronize()
+        """Blocks until the slot's result has landed in pinned host memory and returns that buffer (a slot's stream carries
+        that slot's batches only, so waiting for the stream is waiting for the slot: no per-submit event needed)."""
+        self.streams[slot].synchronize()
         return self.out_h[slot]
 
     def drain(self):
