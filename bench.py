@@ -368,6 +368,7 @@ def main():
     ap.add_argument('--batch', type=int, default=4096)
     ap.add_argument('--humans', type=int, default=5)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--zero-copy', action='store_true', help='e2e: the kernel writes H into pinned host memory itself')
     ap.add_argument('--host-depth', type=int, default=4, help='e2e: batches in flight through hostio.HostStream')
     ap.add_argument('--streams', type=int, default=4, help='CUDA streams the independent steps are issued on')
     args = ap.parse_args()
@@ -517,7 +518,7 @@ def main():
     robots_p = [r.pin_memory() for r in robots[:npin]]
     humans_p = [h.pin_memory() for h in humans[:npin]]
     depth = args.host_depth
-    hs = HostStream(args.workload, module, B, nh, dev, depth=depth)
+    hs = HostStream(args.workload, module, B, nh, dev, depth=depth, zero_copy_out=args.zero_copy)
     for i in range(max(W, npin * depth)):            # warm-up also captures the per-(slot, buffer) graphs
         hs.submit(robots_p[i % npin], humans_p[i % npin])
     hs.drain()

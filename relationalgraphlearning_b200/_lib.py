@@ -113,7 +113,8 @@ def ptr(t):
     """Device pointer of a contiguous fp32/fp64/int32 CUDA tensor (None -> NULL)."""
     if t is None:
         return None
-    assert t.is_cuda and t.is_contiguous(), 'librgl_b200 takes contiguous CUDA tensors'
+    # pinned host memory is device-addressable too (unified virtual addressing): zero-copy outputs
+    assert (t.is_cuda or t.is_pinned()) and t.is_contiguous(), 'librgl_b200 takes contiguous CUDA (or pinned host) tensors'
     return ctypes.c_void_p(t.data_ptr())
 
 

@@ -96,13 +96,13 @@ class RGL(nn.Module):
     def param_tensors(self):
         return ops._graph_param_list(self)
 
-    def run(self, robot, humans, humans_bcast=1, motion_blob=None, want_H=False, want_E=False, want_S=False, throughput=False):
+    def run(self, robot, humans, humans_bcast=1, motion_blob=None, want_H=False, want_E=False, want_S=False, throughput=False, out_H=None):
         """Kernel launch (no autograd).  Records the device-side attention of sample 0 for `.A`."""
         want_A0 = not self.layerwise_graph
         out = ops.graph_forward_raw(ops.packed_graph(self), self.num_layer,
                                     self.flags() | (_lib.FLAG_THROUGHPUT if throughput else 0), robot, humans,
                                     humans_bcast=humans_bcast, mblob=motion_blob, want_H=want_H, want_E=want_E,
-                                    want_S=want_S, want_A0=want_A0)
+                                    want_S=want_S, want_A0=want_A0, out_H=out_H)
         if want_A0:
             self._A_dev, self._A_host = out['A0'], None
         return out

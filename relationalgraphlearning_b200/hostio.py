@@ -17,7 +17,7 @@ class HostStream(object):
     KINDS = ('graph', 'value', 'statepred')
     MAX_GRAPHS = 512
 
-    def __init__(self, kind, module, batch, human_num, device, depth=3, use_graphs=True):
+    def __init__(self, kind, module, batch, human_num, device, depth=3, use_graphs=True, zero_copy_out=False):
         assert kind in self.KINDS
         self.kind, self.module, self.B, self.Nh, self.dev, self.depth = kind, module, batch, human_num, torch.device(device), depth
         n = human_num + 1
@@ -28,6 +28,9 @@ class HostStream(object):
         self.out_h = [torch.empty(self.out_shape).pin_memory() for _ in range(depth)]
         self.graphs = {}
         self.use_graphs = use_graphs
+        # kind 'graph' only: the kernel writes H straight into the pinned result buffer (no separate device->host copy).
+        # Measured on B200 / PCIe Gen5: 59 M states/s against 62-65 M with the copy engine, hence off by default.
+        self.zero_copy_out = bool(zero_copy_out) and kind == 'graph'
         self.count = 0
         self.h2d_bytes = batch * (9 + 5 * human_num) * 4
         self.d2h_bytes = 4
@@ -43,6 +46,8 @@ class HostStream(object):
     def _sequence(self, k, robot_h, humans_h):
         self.robot_d[k].copy_(robot_h, non_blocking=True)
         self.humans_d[k].copy_(humans_h, non_blocking=True)
+        if self.zero_copy_out:
+            return self.module.run(self.robot_d[k], self.humans_d[k], want_H=True, throughput=True, out_H=self.out_h[k])['H']
         out = self._run(self.robot_d[k], self.humans_d[k])
         self.out_h[k].copy_(out, non_blocking=True)
         return out
@@ -71,7 +76,8 @@ class HostStream(object):
                 g.replay()
             else:
                 out = self._sequence(k, robot_h, humans_h)
-                out.record_stream(s)
+                if out.is_cuda:
+                    out.record_stream(s)
         return k
 
     def result(self, slot):

@@ -118,8 +118,10 @@ def _check_state(robot, humans):
 
 
 def graph_forward_raw(gblob, num_layer, flags, robot, humans, humans_bcast=1, mblob=None,
-                      want_H=False, want_E=False, want_S=False, want_A0=False):
-    """One launch of the fused graph kernel.  Returns dict with the requested outputs."""
+                      want_H=False, want_E=False, want_S=False, want_A0=False, out_H=None):
+    """One launch of the fused graph kernel.  Returns dict with the requested outputs.  `out_H` (optional): a preallocated
+    [B,n,32] fp32 buffer for H -- device memory, or pinned host memory (the kernel then streams H over PCIe itself:
+    zero-copy, unified virtual addressing)."""
     robot, humans = _check_state(robot, humans)
     B, Nh = robot.size(0), humans.size(1)
     assert humans.size(0) * humans_bcast >= B
@@ -127,7 +129,10 @@ def graph_forward_raw(gblob, num_layer, flags, robot, humans, humans_bcast=1, mb
     dev = robot.device
     out = {}
     if want_H:
-        out['H'] = torch.empty(B, n, 32, dtype=torch.float32, device=dev)
+        if out_H is not None:
+            assert out_H.dtype == torch.float32 and out_H.is_contiguous() and tuple(out_H.shape) == (B, n, 32)
+            assert out_H.is_cuda or out_H.is_pinned(), 'out_H must be device or pinned host memory'
+        out['H'] = out_H if out_H is not None else torch.empty(B, n, 32, dtype=torch.float32, device=dev)
     if want_E:
         out['E'] = torch.empty(B, 32, dtype=torch.float32, device=dev)
     if want_S:
