@@ -7,26 +7,12 @@
 //   operand in TMEM;  the per-state products run on the FMA pipe with the neighbours' rows in a swizzled shared-memory
 //   buffer;  the output tile (one contiguous HBM block) is staged and written as 512 contiguous bytes per warp instruction.
 //   The weight tiles (UMMA SWIZZLE_128B, hi / lo) are built in shared memory by the CTA from the nn.Parameter layout.
-#include <cuda.h>          // CUtensorMap (types only: cuTensorMapEncodeTiled is fetched through cudaGetDriverEntryPoint)
 #include <stdlib.h>
 #include "kernels.h"
 #include "tc_common.cuh"
+#include "tma_maps.cuh"
 
 namespace rgl {
-
-// ---- TMA tensor copies (2-D tiles of the [rows][32] fp32 feature matrix, SWIZZLE_128B: the hardware lands the rows in
-// shared memory in exactly the chunk ^ (row & 7) pattern the UMMA tiles and the row-per-thread LDS/STS use) ----
-__device__ __forceinline__ void tma_load_2d(uint32_t dst_s, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 :: "r"(dst_s), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, uint32_t src_s) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
-                 :: "l"(map), "r"(c0), "r"(c1), "r"(src_s) : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t gl_row_ptr(uint32_t xf_s, int row) { return xf_s + row * 128 + ((row & 7) << 4); }
 
@@ -443,31 +429,6 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) gcn_layer_tma_kernel(
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tbase, 128 * G);
-}
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn encode_tiled_fn() {
-    static EncodeTiledFn fn = []() -> EncodeTiledFn {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
-            return nullptr;
-        return reinterpret_cast<EncodeTiledFn>(p);
-    }();
-    return fn;
-}
-// [rows][32] fp32 matrix, box = box_rows x 32, SWIZZLE_128B
-static bool make_row_map(CUtensorMap* m, const float* base, long rows, int box_rows) {
-    EncodeTiledFn enc = encode_tiled_fn();
-    if (!enc) return false;
-    const cuuint64_t dims[2] = {32, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {128};
-    const cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
-    const cuuint32_t estr[2] = {1, 1};
-    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 template <int N, int G>

@@ -26,8 +26,10 @@
 //   per-state work (similarity row, softmax, A.(HW)) stays on the FMA pipe (packed FFMA2), one node row per thread,
 //             neighbours' rows read from the group's padded shared-memory buffer; attention weights never leave registers.
 #include <stdlib.h>
+#include <string.h>
 #include "kernels.h"
 #include "tc_common.cuh"
+#include "tma_maps.cuh"
 
 namespace rgl {
 
@@ -58,7 +60,8 @@ constexpr int TC_COLS = 128;          // TMEM columns per group: [0,64) accumula
 constexpr int C_D = 0, C_AHI = 64, C_ALO = 96;
 
 template <int N, int G>
-__global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tc_kernel(const GraphArgs a) {
+__global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tc_kernel(const GraphArgs a, const __grid_constant__ CUtensorMap mapHr,
+                                                                                     const __grid_constant__ CUtensorMap mapHh, const int tma_out) {
     constexpr int NMAX = N > 0 ? N : RGL_MAX_HUMANS + 1;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     float* smem = reinterpret_cast<float*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
@@ -73,7 +76,7 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tc_kern
     uint64_t* bars = reinterpret_cast<uint64_t*>(xf_all + G * (XF_GROUP / 4));      // [0],[1] weights; [2+g] group g
     uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 2 + G);
 
-    const int tid = threadIdx.x, lane = tid & 31, gt = tid & 127;
+    const int tid = threadIdx.x, gt = tid & 127;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // warp-uniform for the compiler
     const int grp = warp >> 2, wq = warp & 3;
     const bool skip = a.flags & RGL_FLAG_SKIP, layerwise = a.flags & RGL_FLAG_LAYERWISE;
@@ -163,6 +166,7 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tc_kern
         const long s0 = (long)tile * SPT;
         const int cnt = (int)min((long)SPT, (long)a.B - s0);
         const bool valid = row_used && s_loc < cnt;
+        if (tma_out && gt == 0) tma_store_wait_read();      // the previous tile's tensor stores have read the staging rows
 #ifdef RGL_TC_TRACE
         tprev = clock64();
         if (grp == 0 && gt == 32) atomicAdd(&g_tc_trace[31], 1ull);
@@ -425,27 +429,44 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tc_kern
             }
         }
         if (a.H != nullptr) {
-            // stage the final rows in xf, then copy out in HBM order: 512 contiguous bytes per warp instruction
-            // (measured faster than each thread streaming its own 128-byte row: 924 vs 854 M states/s at B = 1 M)
             group_sync();                                    // every read of the last H W rows is done
-            TC_MARK(13);   // after: group_sync()
-            xf_store_row(my_row, x);
-            group_sync();
-            TC_MARK(14);   // after: group_sync()
-            float* dst = a.H + s0 * n * XD;
-            const int chunks = cnt * n * 8;
-            for (int idx = gt; idx < chunks; idx += 128) {
-                const int orow = idx >> 3, c = idx & 7;
-                const int s = orow / n, i = orow - s * n;
-                const int srow = i == 0 ? s : SPT + s * Nh + i - 1;
-                *reinterpret_cast<float4*>(dst + (size_t)idx * 4) = lds128s(row_ptr(xf_s, srow) + c * 16);
+            if (tma_out) {
+                // dense SWIZZLE_128B staging (robot rows at [0,SPT), human rows from the next multiple of 8 rows, so both boxes
+                // start 1 KB aligned); two tensor stores (node 0 of SPT states; nodes 1..Nh of SPT states) write the tile in
+                // HBM order, clipped to the batch by the tensor map
+                const int hb8 = (SPT + 7) & ~7;
+                const int srow = is_robot ? gt : hb8 + hrow;
+                const uint32_t rp = xf_s + srow * 128;
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    sts128s(rp + (((c ^ srow) & 7) << 4), make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]));
+                fence_proxy_async();
+                group_sync();
+                if (gt == 0) {
+                    tma_store_3d(&mapHr, 0, 0, (int)s0, xf_s);
+                    tma_store_3d(&mapHh, 0, 1, (int)s0, xf_s + hb8 * 128);
+                    tma_commit();
+                }
+            } else {
+                // stage the final rows in xf, then copy out in HBM order: 512 contiguous bytes per warp instruction
+                xf_store_row(my_row, x);
+                group_sync();
+                float* dst = a.H + s0 * n * XD;
+                const int chunks = cnt * n * 8;
+                for (int idx = gt; idx < chunks; idx += 128) {
+                    const int orow = idx >> 3, c = idx & 7;
+                    const int s = orow / n, i = orow - s * n;
+                    const int srow = i == 0 ? s : SPT + s * Nh + i - 1;
+                    *reinterpret_cast<float4*>(dst + (size_t)idx * 4) = lds128s(row_ptr(xf_s, srow) + c * 16);
+                }
             }
-            // the next tile writes xf only after further group barriers: no extra barrier needed here
+            // the next tile writes xf only after further group barriers (and after thread 0 has seen the stores read it)
         }
         load_raw(tile + tstride);            // next tile's raw rows (prefetched into L2 above): consumed at the top of the loop
     }
 
     // teardown: the bulk copies must have landed before the CTA's shared memory is released
+    if (tma_out && gt == 0) tma_store_wait_all();
     if (tid == 0) { mbar_wait(bars + 0, 0); mbar_wait(bars + 1, 0); }
     tc_fence_before();
     __syncthreads();
@@ -472,7 +493,15 @@ static cudaError_t launch_tc(const GraphArgs& a, int num_sms, size_t max_smem, c
     if (per_sm < 1) per_sm = 1;
     const int want = (b.ntiles + G - 1) / G;
     const int grid = want < num_sms * per_sm ? want : num_sms * per_sm;
-    graph_forward_tc_kernel<N, G><<<grid, 128 * G, smem, st>>>(b);
+    // H leaves through TMA tensor stores when the driver offers cuTensorMapEncodeTiled (RGL_TC_TMA_OUT=0 disables: experiments)
+    static const char* tma_env = getenv("RGL_TC_TMA_OUT");
+    CUtensorMap mr, mh;
+    memset(&mr, 0, sizeof(mr));
+    memset(&mh, 0, sizeof(mh));
+    int tma_out = 0;
+    if (a.H != nullptr && !(tma_env && tma_env[0] == '0'))
+        tma_out = make_state_map(&mr, a.H, a.B, n, 1, spt) && make_state_map(&mh, a.H, a.B, n, n - 1, spt) ? 1 : 0;
+    graph_forward_tc_kernel<N, G><<<grid, 128 * G, smem, st>>>(b, mr, mh, tma_out);
     return cudaGetLastError();
 }
 
