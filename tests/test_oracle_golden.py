@@ -7,6 +7,7 @@ import torch
 from conftest import FWD_CASES, graph_kw, load_golden
 from oracle import planner_oracle as P
 from oracle import rgl_oracle as O
+from oracle import rgl_oracle_np as ON
 
 
 @pytest.mark.parametrize('case', FWD_CASES)
@@ -36,6 +37,30 @@ def test_forward_fp64_arbiter(case):
         S = O.statepred_forward(O.to_double(g['graph2']), O.to_double(g['motion']), r, h, **kw)
     for got, ref in ((H, g['H64']), (V, g['V64']), (S, g['S64'])):
         assert float((got - ref).abs().max()) <= 1e-10 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize('case', FWD_CASES)
+def test_numpy_restatement_matches_reference(case):
+    """The independent NumPy restatement (einsum / exp / sum, no ATen ops) against the reference-minted fixtures: fp64 to
+    round-off against the fp64 outputs, fp32 within the parity tolerance (1e-5 of the tensor scale) against the fp32 ones."""
+    g = load_golden(case)
+    kw = graph_kw(g)
+
+    def np_sd(sd, dt):
+        return {k: v.numpy().astype(dt) for k, v in sd.items()}
+
+    for dt, keys, tol in ((np.float64, ('H64', 'V64', 'S64'), 1e-10), (np.float32, ('H', 'V', 'S'), 1e-5)):
+        r, h = g['robot'].numpy().astype(dt), g['humans'].numpy().astype(dt)
+        g1, g2 = np_sd(g['graph1'], dt), np_sd(g['graph2'], dt)
+        H, A0 = ON.rgl_forward(g1, r, h, return_A=True, **kw)
+        V = ON.value_forward(g1, np_sd(g['value'], dt), r, h, **kw)
+        S = ON.statepred_forward(g2, np_sd(g['motion'], dt), r, h, **kw)
+        for got, key in ((H, keys[0]), (V, keys[1]), (S, keys[2])):
+            ref = g[key].numpy().astype(np.float64)
+            assert got.shape == ref.shape and got.dtype == dt
+            assert np.abs(got.astype(np.float64) - ref).max() <= tol * max(1e-3, np.abs(ref).max()), (case, key, dt)
+        if dt == np.float32 and g['A0'].numel():
+            assert np.abs(A0[0] - g['A0'].numpy()).max() <= 1e-5
 
 
 def test_action_space_matches_reference():
