@@ -2,7 +2,8 @@
 
 The number of 128-row groups per CTA (1 / 2 / 4) is normally chosen from the batch size and the requested outputs; the
 experiment switch RGL_TC_GROUPS forces it, RGL_GRAPH_VARIANT selects the legacy fp32-FMA / mma.sync kernels, and
-RGL_VALUE_VARIANT / RGL_TC_VALUE_GROUPS do the same for the value head.  They are read once per process, so each variant runs in a child process: graph / value / state-predictor outputs against the CPU
+RGL_VALUE_VARIANT / RGL_TC_VALUE_GROUPS do the same for the value head; RGL_TC_TMA_OUT=0 selects the staged copy-out of H
+instead of the TMA tensor stores.  They are read once per process, so each variant runs in a child process: graph / value / state-predictor outputs against the CPU
 oracle on batches large enough that every group loops over several tiles, with a ragged last tile.
 Tolerance: |x - ref| <= 1e-5 * max(|ref|, max|ref|)."""
 import os
@@ -70,8 +71,8 @@ print('variant ok')
 @pytest.mark.parametrize('env', [{'RGL_TC_GROUPS': '1'}, {'RGL_TC_GROUPS': '2'}, {'RGL_TC_GROUPS': '4'}, {},
                                  {'RGL_GRAPH_VARIANT': 'm'}, {'RGL_GRAPH_VARIANT': '4', 'RGL_GCN_VARIANT': 'f'},
                                  {'RGL_VALUE_VARIANT': 't', 'RGL_TC_VALUE_GROUPS': '1'}, {'RGL_VALUE_VARIANT': 't', 'RGL_TC_VALUE_GROUPS': '2'},
-                                 {'RGL_VALUE_VARIANT': 'f'}],
-                         ids=['tc_g1', 'tc_g2', 'tc_g4', 'tc_auto', 'legacy_mma', 'legacy_ffma', 'value_tc_g1', 'value_tc_g2', 'value_ffma'])
+                                 {'RGL_VALUE_VARIANT': 'f'}, {'RGL_TC_TMA_OUT': '0'}],
+                         ids=['tc_g1', 'tc_g2', 'tc_g4', 'tc_auto', 'legacy_mma', 'legacy_ffma', 'value_tc_g1', 'value_tc_g2', 'value_ffma', 'staged_copy_out'])
 def test_kernel_variant_against_oracle(env):
     if not torch.cuda.is_available():
         pytest.skip('no CUDA device')
@@ -80,6 +81,7 @@ def test_kernel_variant_against_oracle(env):
     e.pop('RGL_GRAPH_VARIANT', None)
     e.pop('RGL_VALUE_VARIANT', None)
     e.pop('RGL_GCN_VARIANT', None)
+    e.pop('RGL_TC_TMA_OUT', None)
     e.pop('RGL_TC_VALUE_GROUPS', None)
     e.update(env)
     res = subprocess.run([sys.executable, '-c', CHILD % {'root': ROOT}], env=e, capture_output=True, text=True, timeout=240)
