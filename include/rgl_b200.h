@@ -198,6 +198,32 @@ int rgl_attn_layer_bwd(const float* A, const float* Hprev, const float* gM, cons
 int rgl_sim_bwd(const float* A, const float* gA, const float* X, const float* Y, float* gY, float* gX,
                 int B, int n, rgl_stream_t stream);
 
+/* ---- data-parallel gradient exchange (one process per GPU, NVLink peer memory) ----------------------------------
+ * Data-parallel form of crowd_nav/utils/trainer.py:122-131,143-149: every rank back-propagates its shard of the
+ * minibatch, then ONE sum over a flat fp32 buffer holding every gradient (22 813 floats = 91 252 B for the value
+ * estimator).  The reference has no multi-process code; this handle is the per-rank workspace the
+ * boundary allows (rgl_*_create / _destroy).
+ *   rgl_comm_create      allocates (cudaMalloc, zeroed) the local accumulation buffer, receive slots and flags;
+ *   rgl_comm_ipc_handle  writes rgl_comm_handle_bytes() bytes that identify the allocation to other processes
+ *                        (exchange them with any host-side all-gather, e.g. torch.distributed);
+ *   rgl_comm_open_peers  maps every peer's allocation (handles = world x rgl_comm_handle_bytes(), rank order);
+ *   rgl_comm_accum_ptr   DEVICE pointer of the local accumulation buffer [nfloats]: the backward kernels
+ *                        (rgl_linear_bwd dW/db) accumulate straight into it;
+ *   rgl_comm_allreduce   one kernel on `stream`: out[i] = scale * sum_over_ranks accum_r[i] (summed in rank order: the
+ *                        same bits on every rank), then accum is re-zeroed.  No host synchronisation, CUDA-graph
+ *                        capturable; every rank must launch it the same number of times;
+ *   rgl_comm_status      0 = ok, 1 = a peer did not arrive within ~10 s (synchronises the device). */
+typedef struct RglComm RglComm;
+int    rgl_comm_create(int rank, int world, long long nfloats, RglComm** out);
+int    rgl_comm_handle_bytes(void);
+int    rgl_comm_ipc_handle(RglComm* c, void* handle_out);
+int    rgl_comm_open_peers(RglComm* c, const void* handles);
+float* rgl_comm_accum_ptr(RglComm* c);
+int    rgl_comm_allreduce(RglComm* c, float* out, float scale, rgl_stream_t stream);
+int    rgl_comm_status(RglComm* c, int* status);
+int    rgl_comm_destroy(RglComm* c);
+const char* rgl_comm_last_error_string(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,6 +78,16 @@ EXPORTS = {
                                        ctypes.c_int, ctypes.c_double, c_float_p, c_float_p, ctypes.c_void_p]),
     'rgl_plan_argmax': (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                        c_float_p, ctypes.c_void_p, ctypes.c_void_p]),
+    # data-parallel gradient exchange over NVLink peer memory (csrc/dp_comm.cu)
+    'rgl_comm_create': (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_longlong, ctypes.POINTER(ctypes.c_void_p)]),
+    'rgl_comm_handle_bytes': (ctypes.c_int, []),
+    'rgl_comm_ipc_handle': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    'rgl_comm_open_peers': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    'rgl_comm_accum_ptr': (ctypes.c_void_p, [ctypes.c_void_p]),
+    'rgl_comm_allreduce': (ctypes.c_int, [ctypes.c_void_p, c_float_p, ctypes.c_float, ctypes.c_void_p]),
+    'rgl_comm_status': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)]),
+    'rgl_comm_destroy': (ctypes.c_int, [ctypes.c_void_p]),
+    'rgl_comm_last_error_string': (ctypes.c_char_p, []),
 }
 
 _lib = None
@@ -103,9 +113,9 @@ def lib():
     return _lib
 
 
-def check(rc, what):
+def check(rc, what, comm=False):
     if rc != 0:
-        msg = lib().rgl_last_error_string()
+        msg = lib().rgl_comm_last_error_string() if comm else lib().rgl_last_error_string()
         raise RglError('%s failed (rc=%d): %s' % (what, rc, msg.decode() if msg else ''))
 
 

@@ -8,9 +8,24 @@ the host never blocks until it asks for a result.
 
 The per-batch sequence is captured ONCE per (slot, host buffer) into a CUDA graph (memcpy nodes + kernel
 nodes) and replayed afterwards: a submit costs one cudaGraphLaunch instead of ~10 Python-level CUDA calls.
-Host buffers that were not seen before (or are not pinned) take the same path eagerly.
+Host buffers that were not seen before (or are not pinned) take the same path eagerly.  The cache holds at most
+MAX_GRAPHS graphs and evicts the least recently used one.
+
+Back-pressure: a slot's pinned result buffer is reused `depth` submits later (stream-ordered behind the slot's previous
+batch).  A consumer that wants every result calls `result(slot)` at most `depth - 1` submits after the `submit()` that
+returned the slot -- i.e. it keeps at most `depth` batches in flight; `overwritten` counts results whose slot was
+re-submitted before anybody fetched them.
+
+Weights: the captured graphs read the modules' packed weight blobs in place, so every submit re-runs the cheap
+(data_ptr, _version) check of the wrapped module and re-packs into the same blob, ordered before the replay on the
+slot's stream, when an optimizer step or load_state_dict changed a parameter (batches of OTHER slots that are still in
+flight at that moment may see either version: drain() first when that matters).
 """
+import collections
+
 import torch
+
+from . import ops
 
 
 class HostStream(object):
@@ -26,7 +41,7 @@ class HostStream(object):
         self.robot_d = [torch.empty(batch, 1, 9, device=self.dev) for _ in range(depth)]
         self.humans_d = [torch.empty(batch, human_num, 5, device=self.dev) for _ in range(depth)]
         self.out_h = [torch.empty(self.out_shape).pin_memory() for _ in range(depth)]
-        self.graphs = {}
+        self.graphs = collections.OrderedDict()
         self.use_graphs = use_graphs
         # kind 'graph' only: the kernel writes H straight into the pinned result buffer (no separate device->host copy).
         # Measured on B200 / PCIe Gen5: 59 M states/s against 62-65 M with the copy engine, hence off by default.
@@ -37,11 +52,25 @@ class HostStream(object):
         for d in self.out_shape:
             self.d2h_bytes *= d
         self._warm = False
+        self._pending = [False] * depth       # slot holds a result nobody fetched yet
+        self.overwritten = 0
 
     def _run(self, robot, humans):
         if self.kind == 'graph':
             return self.module.run(robot, humans, want_H=True, throughput=True)['H']
         return self.module.run(robot, humans, throughput=True)
+
+    def _refresh_weights(self):
+        """Re-pack (in place, on the current stream) any blob whose parameters changed since it was packed."""
+        m = self.module
+        if self.kind == 'graph':
+            ops.packed_graph(m)
+            return
+        ops.packed_graph(m.graph_model)
+        if self.kind == 'value':
+            ops.packed_value(m.value_network, m._pack_cache)
+        else:
+            ops.packed_motion(m.human_motion_predictor, m._pack_cache)
 
     def _sequence(self, k, robot_h, humans_h):
         self.robot_d[k].copy_(robot_h, non_blocking=True)
@@ -58,21 +87,28 @@ class HostStream(object):
         k = self.count % self.depth
         self.count += 1
         s = self.streams[k]
+        if self._pending[k]:
+            self.overwritten += 1             # the slot's previous result was never fetched and is about to be replaced
+        self._pending[k] = True
         with torch.cuda.stream(s), torch.no_grad():
             if not self._warm:                      # first call: pack weights, load the module, size the pools
                 self._sequence(k, robot_h, humans_h)
                 s.synchronize()
                 self._warm = True
+            self._refresh_weights()
             key = (k, robot_h.data_ptr(), humans_h.data_ptr())
             g = self.graphs.get(key) if self.use_graphs else None      # a cached graph implies the buffers were pinned at capture
             pinned = g is not None or (self.use_graphs and robot_h.is_pinned() and humans_h.is_pinned())
-            if g is None and pinned and len(self.graphs) < self.MAX_GRAPHS:
+            if g is None and pinned:
+                if len(self.graphs) >= self.MAX_GRAPHS:
+                    self.graphs.popitem(last=False)                    # least recently used
                 s.synchronize()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=s):
                     self._keep = self._sequence(k, robot_h, humans_h)
                 self.graphs[key] = g
             if g is not None:
+                self.graphs.move_to_end(key)
                 g.replay()
             else:
                 out = self._sequence(k, robot_h, humans_h)
@@ -82,8 +118,10 @@ class HostStream(object):
 
     def result(self, slot):
         """Blocks until the slot's result has landed in pinned host memory and returns that buffer (a slot's stream carries
-        that slot's batches only, so waiting for the stream is waiting for the slot: no per-submit event needed)."""
+        that slot's batches only, so waiting for the stream is waiting for the slot: no per-submit event needed).  The
+        buffer is valid until the next submit() that maps to the same slot."""
         self.streams[slot].synchronize()
+        self._pending[slot] = False
         return self.out_h[slot]
 
     def drain(self):

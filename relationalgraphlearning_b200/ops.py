@@ -60,14 +60,14 @@ def _graph_param_list(rgl):
 
 
 def packed_graph(rgl):
-    params = [p.detach() for p in _graph_param_list(rgl)]
+    params = _graph_param_list(rgl)          # (the cache key reads data_ptr / _version only: no detach() on the fast path)
     L = len(rgl.Ws)
     lib = _lib.lib()
 
     def pack(blob):
         gp = _lib.GraphParams()
         names = ['wr0_w', 'wr0_b', 'wr1_w', 'wr1_b', 'wh0_w', 'wh0_b', 'wh1_w', 'wh1_b', 'w_a']
-        keep = [_f32c(p) for p in params]
+        keep = [_f32c(p.detach()) for p in params]
         for nme, t in zip(names, keep[:9]):
             setattr(gp, nme, t.data_ptr())
         for i in range(L):
@@ -81,12 +81,11 @@ def packed_graph(rgl):
 def packed_value(seq, cache):
     params = [seq[0].weight, seq[0].bias, seq[2].weight, seq[2].bias, seq[4].weight, seq[4].bias,
               seq[6].weight, seq[6].bias]
-    params = [p.detach() for p in params]
     lib = _lib.lib()
 
     def pack(blob):
         vp = _lib.ValueParams()
-        keep = [_f32c(p) for p in params]
+        keep = [_f32c(p.detach()) for p in params]
         for nme, t in zip(['w0', 'b0', 'w1', 'b1', 'w2', 'b2', 'w3', 'b3'], keep):
             setattr(vp, nme, t.data_ptr())
         _lib.check(lib.rgl_pack_value(ctypes.byref(vp), _lib.ptr(blob), _lib.stream_ptr(blob.device)), 'rgl_pack_value')
@@ -95,12 +94,12 @@ def packed_value(seq, cache):
 
 
 def packed_motion(seq, cache):
-    params = [p.detach() for p in (seq[0].weight, seq[0].bias, seq[2].weight, seq[2].bias)]
+    params = [seq[0].weight, seq[0].bias, seq[2].weight, seq[2].bias]
     lib = _lib.lib()
 
     def pack(blob):
         mp = _lib.MotionParams()
-        keep = [_f32c(p) for p in params]
+        keep = [_f32c(p.detach()) for p in params]
         for nme, t in zip(['w0', 'b0', 'w1', 'b1'], keep):
             setattr(mp, nme, t.data_ptr())
         _lib.check(lib.rgl_pack_motion(ctypes.byref(mp), _lib.ptr(blob), _lib.stream_ptr(blob.device)), 'rgl_pack_motion')

@@ -39,48 +39,194 @@ def gather_results(local, total, group=None):
 
 
 class FlatGradAllReducer(object):
-    """Sum-all-reduce of all gradients of `params` through one flat buffer (one collective per optimizer step)."""
+    """Generic sum-all-reduce of the gradients autograd left in `p.grad`, through one flat buffer (one collective per
+    optimizer step).  Used for modules without the native backward (CPU / gloo tests, layerwise graphs); the product
+    path is FlatGrads below, where no gather / scatter copies exist at all."""
 
     def __init__(self, params, group=None):
         self.params = [p for p in params if p.requires_grad]
         self.group = group
         self.numel = sum(p.numel() for p in self.params)
         self.buf = None
+        self.views = None
+
+    def step_begin(self, optimizer=None):
+        if optimizer is not None:
+            optimizer.zero_grad()
 
     def reduce(self):
         dev = self.params[0].device
         if self.buf is None or self.buf.device != dev:
             self.buf = torch.zeros(self.numel, dtype=torch.float32, device=dev)
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            if p.grad is None:
-                self.buf[off:off + n].zero_()
-            else:
-                self.buf[off:off + n].copy_(p.grad.reshape(-1))
-            off += n
-        dist.all_reduce(self.buf, op=dist.ReduceOp.SUM, group=self.group)
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            g = self.buf[off:off + n].view_as(p)
-            if p.grad is None:
-                p.grad = g.clone()
-            else:
-                p.grad.copy_(g)
-            off += n
+            self.views, off = [], 0
+            for p in self.params:
+                self.views.append(self.buf[off:off + p.numel()].view_as(p))
+                off += p.numel()
+        have = [(v, p.grad) for v, p in zip(self.views, self.params) if p.grad is not None and p.grad.data_ptr() != v.data_ptr()]
+        if len(have) < len(self.params):
+            for v, p in zip(self.views, self.params):
+                if p.grad is None:
+                    v.zero_()
+        if have:
+            torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+        if dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(self.buf, op=dist.ReduceOp.SUM, group=self.group)
+        for v, p in zip(self.views, self.params):
+            p.grad = v                      # the optimizer reads the reduced gradients in place (no scatter copies)
         return self.buf
+
+
+class _DevMem(object):
+    """Raw device memory as a __cuda_array_interface__ exporter (torch.as_tensor wraps it without copying)."""
+
+    def __init__(self, ptr, nfloats):
+        self.__cuda_array_interface__ = {'shape': (nfloats,), 'typestr': '<f4', 'data': (int(ptr), False), 'version': 2}
+
+
+class FlatGrads(object):
+    """Every gradient of a ValueEstimator / StatePredictor in ONE flat fp32 buffer, written there by the backward kernels.
+
+      accum   where training.py's native backward accumulates (rgl_linear_bwd dW / db atomics): `module._grad_sink`
+      grad    the reduced gradients; every `p.grad` is a view into it, so the optimizer reads them in place
+      reduce  world == 1: nothing (grad IS accum).  world > 1: ONE collective over the flat buffer --
+              backend 'p2p'  : rgl_comm_allreduce, the one-kernel push all-reduce over NVLink peer memory
+                               (csrc/dp_comm.cu; accum lives in the cudaIpc-shared workspace; CUDA-graph capturable),
+              backend 'nccl' : torch.distributed.all_reduce on `accum` in place (also capturable).
+    'auto' picks p2p when the peer-memory rendezvous succeeds on every rank and NCCL otherwise.
+    """
+
+    def __init__(self, module, group=None, backend='auto', params=None):
+        from . import _lib
+        self.module = module
+        self.params = [p for p in (params if params is not None else module.parameters()) if p.requires_grad]
+        self.group = group
+        self.dev = self.params[0].device
+        self.numel = sum(p.numel() for p in self.params)
+        self.offsets, off = {}, 0
+        for p in self.params:
+            self.offsets[id(p)] = off
+            off += (p.numel() + 3) & ~3                  # 16-byte aligned views
+        self.nfloats = off
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.comm = None
+        self.backend = 'local'
+        self.fallback_reason = None
+        if self.world > 1:
+            want = backend
+            if want in ('auto', 'p2p') and self.dev.type == 'cuda':
+                try:
+                    self._open_p2p(_lib)
+                    self.backend = 'p2p'
+                except Exception as e:  # noqa: BLE001
+                    if want == 'p2p':
+                        raise
+                    self.fallback_reason = str(e)
+            if self.backend != 'p2p':
+                self.backend = 'nccl'
+        if self.backend == 'p2p':
+            ptr = _lib.lib().rgl_comm_accum_ptr(self.comm)
+            self._mem = _DevMem(ptr, self.nfloats)
+            self.accum = torch.as_tensor(self._mem, device=self.dev)
+            self.grad = torch.zeros(self.nfloats, dtype=torch.float32, device=self.dev)
+        else:
+            self.accum = torch.zeros(self.nfloats, dtype=torch.float32, device=self.dev)
+            self.grad = self.accum
+        self.accum_views = {id(p): self.accum[self.offsets[id(p)]:self.offsets[id(p)] + p.numel()].view_as(p) for p in self.params}
+        self.grad_views = {id(p): self.grad[self.offsets[id(p)]:self.offsets[id(p)] + p.numel()].view_as(p) for p in self.params}
+        self.message_bytes = self.numel * 4
+        module._grad_sink = self
+        self._install()
+
+    # ---- peer-memory rendezvous: create the workspace, all-gather the 64-byte cudaIpc handles, map the peers ----
+    def _open_p2p(self, _lib):
+        import ctypes
+        lib = _lib.lib()
+        with torch.cuda.device(self.dev):
+            h = ctypes.c_void_p()
+            _lib.check(lib.rgl_comm_create(self.rank, self.world, self.nfloats, ctypes.byref(h)), 'rgl_comm_create', comm=True)
+            nb = lib.rgl_comm_handle_bytes()
+            mine = (ctypes.c_ubyte * nb)()
+            _lib.check(lib.rgl_comm_ipc_handle(h, mine), 'rgl_comm_ipc_handle', comm=True)
+            t = torch.tensor(list(mine), dtype=torch.uint8, device=self.dev)
+            outs = [torch.empty_like(t) for _ in range(self.world)]
+            dist.all_gather(outs, t, group=self.group)
+            allh = (ctypes.c_ubyte * (nb * self.world))(*[int(x) for o in outs for x in o.cpu().tolist()])
+            rc = lib.rgl_comm_open_peers(h, allh)
+            ok = torch.tensor([1 if rc == 0 else 0], device=self.dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)      # all ranks agree on the backend
+            if int(ok) == 0:
+                msg = lib.rgl_comm_last_error_string()
+                lib.rgl_comm_destroy(h)
+                raise RuntimeError('peer-memory rendezvous failed on some rank: %s' % (msg.decode() if msg else ''))
+            self.comm = h
+
+    def _install(self):
+        for p in self.params:
+            v = self.grad_views[id(p)]
+            if p.grad is None or p.grad.data_ptr() != v.data_ptr():
+                p.grad = v
+
+    def covers(self, plist):
+        return all(id(p) in self.offsets for p in plist)
+
+    def accum_view(self, p):
+        return self.accum_views[id(p)]
+
+    def step_begin(self, optimizer=None):
+        """Replaces optimizer.zero_grad(): one fill of the flat buffer (p2p: the all-reduce kernel already re-zeroed it)."""
+        if self.backend != 'p2p':
+            self.accum.zero_()
+        self._install()
+
+    def reduce(self):
+        from . import _lib
+        if self.backend == 'p2p':
+            with torch.cuda.device(self.dev):
+                _lib.check(_lib.lib().rgl_comm_allreduce(self.comm, _lib.ptr(self.grad), 1.0, _lib.stream_ptr(self.dev)),
+                           'rgl_comm_allreduce', comm=True)
+            from . import ops
+            ops._count(1)
+        elif self.backend == 'nccl':
+            dist.all_reduce(self.accum, op=dist.ReduceOp.SUM, group=self.group)
+        return self.grad
+
+    def flat_grad(self):
+        """Dense copy of the reduced gradients in parameter order (tests / checks)."""
+        return torch.cat([self.grad_views[id(p)].reshape(-1) for p in self.params])
+
+    def status(self):
+        """0 = ok; 1 = a peer did not arrive at an all-reduce within ~10 s (synchronises)."""
+        if self.comm is None:
+            return 0
+        import ctypes
+        from . import _lib
+        st = ctypes.c_int(0)
+        _lib.check(_lib.lib().rgl_comm_status(self.comm, ctypes.byref(st)), 'rgl_comm_status', comm=True)
+        return int(st.value)
+
+    def close(self):
+        if getattr(self.module, '_grad_sink', None) is self:
+            self.module._grad_sink = None
+        if self.comm is not None:
+            from . import _lib
+            for p in self.params:
+                p.grad = None
+            self.accum_views = self.accum = self._mem = None
+            _lib.lib().rgl_comm_destroy(self.comm)
+            self.comm = None
 
 
 def dp_value_step(value_estimator, target_model, optimizer, reducer, robot, humans, rewards, next_robot, next_humans,
                   gamma_bar, global_batch):
-    """One data-parallel value-network step on this rank's shard (trainer.py:122-131).
+    """One data-parallel value-network step on this rank's shard (trainer.py:122-131).  `reducer`: FlatGrads (native
+    backward writes the flat buffer directly) or FlatGradAllReducer (generic).
 
     MSELoss(mean) over the GLOBAL batch = sum over ranks of (local squared-error sum / global_batch), so each rank
     back-propagates `sum((out - target)^2) / global_batch` and the gradients are summed across ranks.
     Returns the local loss contribution (a tensor; sum over ranks = the global mean loss).
     """
-    optimizer.zero_grad()
+    reducer.step_begin(optimizer)
     out = value_estimator((robot, humans))
     with torch.no_grad():
         target = rewards + gamma_bar * target_model((next_robot, next_humans))
@@ -93,7 +239,7 @@ def dp_value_step(value_estimator, target_model, optimizer, reducer, robot, huma
 
 def dp_state_predictor_step(state_predictor, optimizer, reducer, robot, humans, next_humans, global_batch, detach=False):
     """Data-parallel state-predictor step (trainer.py:143-149): MSE over the global [B,Nh,5] prediction."""
-    optimizer.zero_grad()
+    reducer.step_begin(optimizer)
     _, est = state_predictor((robot, humans), None, detach=detach)
     denom = float(global_batch) * est.size(1) * est.size(2)
     loss = ((est - next_humans) ** 2).sum() / denom

@@ -113,10 +113,23 @@ def _graph_backward(g, sv, robot, humans, gH, G, dev):
                 db=G(g.w_h[0].bias), dev=dev)
 
 
-def _grad_buffers(plist, extra, dev):
-    """Zero-filled flat buffer: [gradients of plist | extra floats].  Returns (dict id(p)->view, extra view)."""
+def _grad_buffers(plist, extra, dev, sink=None):
+    """Gradient buffers of `plist` + `extra` zeroed floats.  Returns (dict id(p)->view, extra view, direct).
+
+    With a flat-gradient sink attached to the module (parallel.FlatGrads) that covers every parameter, the views are
+    slices of the sink's accumulation buffer: the backward kernels accumulate straight into the buffer the gradient
+    all-reduce / optimizer reads (direct = True; autograd then receives no parameter gradients).  Otherwise a fresh
+    zero-filled flat buffer is carved and returned through autograd."""
+    if sink is not None and sink.covers(plist) and sink.dev == dev:
+        return {id(p): sink.accum_view(p) for p in plist}, torch.zeros(extra, dtype=torch.float32, device=dev), True
     v = _carve([p.numel() for p in plist] + [extra], dev, zero=True)
-    return {id(p): v[i].view(p.shape) for i, p in enumerate(plist)}, v[len(plist)]
+    return {id(p): v[i].view(p.shape) for i, p in enumerate(plist)}, v[len(plist)], False
+
+
+def _saved(ctx, what):
+    if ctx.sv is None:
+        raise RuntimeError('%s: the saved activations were freed by the first backward pass; run the forward again '
+                           '(retain_graph=True is not supported by the native training path)' % what)
 
 
 class _ValueTrain(torch.autograd.Function):
@@ -137,12 +150,16 @@ class _ValueTrain(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gV):
+        _saved(ctx, 'ValueEstimator backward')
         ve, sv = ctx.ve, ctx.sv
         g, vn = ve.graph_model, ve.value_network
         robot, humans, E, v0, v1, v2 = ctx.acts
         B, n, dev = robot.size(0), humans.size(1) + 1, robot.device
+        if not any(ctx.needs_input_grad[3:]):            # every parameter frozen (e.g. a target network called under grad)
+            ctx.sv = ctx.acts = None
+            return (None,) * (3 + len(ve._train_params()))
         gV = gV.contiguous().float()
-        gp, gHflat = _grad_buffers(list(g.parameters()) + list(vn.parameters()), B * n * 32, dev)
+        gp, gHflat, direct = _grad_buffers(list(g.parameters()) + list(vn.parameters()), B * n * 32, dev, getattr(ve, '_grad_sink', None))
         G = lambda p: gp[id(p)]   # noqa: E731
         with torch.cuda.device(dev), torch.no_grad():
             t = _carve([B * 128, B * 128, B * 32], dev)
@@ -156,7 +173,7 @@ class _ValueTrain(torch.autograd.Function):
             _linear_bwd(_rows(g0, 32), 32, _rows(E, 32), 32, B, W=vn[0].weight, mask=_rows(v0, 32),
                         Gin=_rows(gH, 32, 1, n * 32), dW=G(vn[0].weight), db=G(vn[0].bias), dev=dev)
             _graph_backward(g, sv, robot, humans, gH, G, dev)
-        grads = [gp[id(p)] for p in ve._train_params()]
+        grads = [None if direct else gp[id(p)] for p in ve._train_params()]
         ctx.sv = ctx.acts = None
         return (None, None, None) + tuple(grads)
 
@@ -173,14 +190,18 @@ class _StatePredTrain(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gS):
+        _saved(ctx, 'StatePredictor backward')
         sp, sv, detach = ctx.sp, ctx.sv, ctx.detach
         g, mp = sp.graph_model, sp.human_motion_predictor
         robot, humans = ctx.acts
         B, Nh, dev = robot.size(0), humans.size(1), robot.device
         n, L = Nh + 1, g.num_layer
+        if not any(ctx.needs_input_grad[4:]):
+            ctx.sv = ctx.acts = None
+            return (None,) * (4 + len(sp._train_params(detach)))
         gS = gS.contiguous().float()
         plist = list(mp.parameters()) + ([] if detach else list(g.parameters()))
-        gp, gHflat = _grad_buffers(plist, B * n * 32, dev)
+        gp, gHflat, direct = _grad_buffers(plist, B * n * 32, dev, getattr(sp, '_grad_sink', None))
         G = lambda p: gp[id(p)]   # noqa: E731
         with torch.cuda.device(dev), torch.no_grad():
             gmh = _carve([B * Nh * 64], dev)[0].view(B * Nh, 64)
@@ -193,7 +214,7 @@ class _StatePredTrain(torch.autograd.Function):
                         dW=G(mp[0].weight), db=G(mp[0].bias), dev=dev)
             if not detach:
                 _graph_backward(g, sv, robot, humans, gH, G, dev)
-        grads = [gp[id(p)] for p in sp._train_params(detach)]
+        grads = [None if direct else gp[id(p)] for p in sp._train_params(detach)]
         ctx.sv = ctx.acts = None
         return (None, None, None, None) + tuple(grads)
 

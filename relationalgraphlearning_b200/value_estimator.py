@@ -23,7 +23,7 @@ class ValueEstimator(nn.Module):
         new = self.__class__.__new__(self.__class__)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            if k != '_pack_cache':
+            if k not in ('_pack_cache', '_grad_sink'):
                 setattr(new, k, copy.deepcopy(v, memo))
         new._pack_cache = ops._PackCache()
         return new

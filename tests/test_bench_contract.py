@@ -18,9 +18,11 @@ def test_reference_arm_prints_the_contract_line():
     d = json.loads(lines[0])
     assert d['impl'] == 'reference' and d['unit'] == 'states/s' and d['higher_is_better'] is True
     assert d['value'] > 0 and d['gpu_launches'] == 0
-    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    from oracle import make_ref
+    assert d['cpu_baseline']['kind'] == ('reference' if make_ref.available() else 'port') and d['cpu_baseline']['cores'] >= 1
+    assert d['cpu_baseline']['cores_available'] >= d['cpu_baseline']['cores']
     assert d['e2e']['value'] == d['value'] and d['e2e']['h2d_bytes_per_step'] == 0
-    assert 'workload' in d['config']
+    assert 'workload' in d['config'] and 'input_pool_mb' in d['config']      # the same config keys in both arms
 
 
 def test_algorithmic_counts_match_the_survey():
