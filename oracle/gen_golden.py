@@ -157,6 +157,79 @@ def planner_case(name, seed, nh, n_states, data_seed=77):
     print('wrote', name, 'chosen', chosen)
 
 
+def load_patched_planner():
+    """crowd_nav/policy/model_predictive_rl_d.py from oracle/_ref: the reference planner with ONE line changed
+    (`values.append(float(value))`, model_predictive_rl.py:250; recipe and rationale in oracle/make_ref.py) so that
+    action_clip / the depth > 1 recursion run on this torch / numpy."""
+    from oracle import make_ref
+    if not make_ref.available():
+        make_ref.make(quiet=True)
+    path = os.path.join(make_ref.OUT, 'crowd_nav', 'policy', 'model_predictive_rl_d.py')
+    spec = importlib.util.spec_from_file_location('crowd_nav.policy.model_predictive_rl_d', path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.ModelPredictiveRL
+
+
+def planner_tree_case(name, seed, nh, n_states, depth, width, sparse=False, speed_samples=5, rotation_samples=16, data_seed=91):
+    """predict() of the reference planner (patched copy, see load_patched_planner) with action clipping at depth > 1:
+    root clipped action set, per-kept-action reward / look-ahead return / value, the chosen action and the action sequence
+    of the best trajectory (model_predictive_rl.py:212-233, 242-302)."""
+    stub_sim_deps()
+    ModelPredictiveRL = load_patched_planner()
+    from crowd_sim.envs.utils.state import FullState, ObservableState, JointState
+    cfg = load_ref_config('mp_separate').PolicyConfig()
+    mp = cfg.model_predictive_rl
+    mp.planning_depth, mp.planning_width, mp.do_action_clip = depth, width, True
+    if sparse:
+        mp.sparse_search = True
+    cfg.action_space.speed_samples, cfg.action_space.rotation_samples = speed_samples, rotation_samples
+    torch.manual_seed(seed)
+    pol = ModelPredictiveRL()
+    pol.configure(cfg)
+    pol.set_time_step(0.25)
+    pol.set_device(torch.device('cpu'))
+    pol.set_phase('test')
+    robot, humans = synthetic_states(n_states, nh, seed=data_seed)
+    humans[1, 0, 0:2] = robot[1, 0, 0:2] + torch.tensor([0.6, 0.1])          # near-collision root
+    robot[2, 0, 0:2] = torch.tensor([0.1, 3.7])                               # near-goal root
+    chosen, kept, values, rewards, rets, trajs = [], [], [], [], [], []
+    with torch.no_grad():
+        for b in range(n_states):
+            r = [float(x) for x in robot[b, 0]]
+            st = JointState(FullState(*r), [ObservableState(*[float(x) for x in humans[b, h]]) for h in range(nh)])
+            act = pol.predict(st)
+            index = {a: i for i, a in enumerate(pol.action_space)}
+            chosen.append(index[act])
+            trajs.append([index[a] for (_, a, _) in pol.get_traj() if a is not None])
+            st_t = st.to_tensor(add_batch_size=True, device=pol.device)
+            clipped = pol.action_clip(st_t, pol.action_space, pol.planning_width)
+            kept.append([index[a] for a in clipped])
+            vals, rews, rts = [], [], []
+            for a in clipped:
+                nxt = pol.state_predictor(st_t, a)
+                ret, _ = pol.V_planning(nxt, pol.planning_depth, pol.planning_width)
+                rew = pol.estimate_reward(st, a)
+                rews.append(float(rew))
+                rts.append(float(ret))
+                vals.append(float(rew + pol.get_normalized_gamma() * ret))
+            values.append(vals); rewards.append(rews); rets.append(rts)
+    actions = np.array([[a.vx, a.vy] for a in pol.action_space], dtype=np.float64)
+    sd = pol.get_state_dict()
+    out = {}
+    out.update(sd_np(sd['graph_model1'], 'graph1/'))
+    out.update(sd_np(sd['value_network'], 'value/'))
+    out.update(sd_np(sd['graph_model2'], 'graph2/'))
+    out.update(sd_np(sd['motion_predictor'], 'motion/'))
+    tl = max(len(t) for t in trajs)
+    out.update(robot=robot.numpy(), humans=humans.numpy(), chosen=np.array(chosen), kept=np.array(kept), values=np.array(values),
+               rewards=np.array(rewards), rets=np.array(rets), traj=np.array([t + [-1] * (tl - len(t)) for t in trajs]),
+               actions=actions, action_group_index=np.array(pol.action_group_index),
+               meta=np.array([seed, nh, n_states, data_seed, depth, width, int(sparse), speed_samples, rotation_samples], dtype=np.int64))
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
+    print('wrote', name, 'chosen', chosen, 'kept', kept, 'traj', trajs)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)
@@ -172,6 +245,11 @@ def main():
     forward_case('fwd_nh5_layerwise_noskip', 0, 5, 64, layerwise=True, skip=False)   # BasePolicyConfig defaults
     forward_case('fwd_nh5_layerwise_skip', 1, 5, 64, layerwise=True, skip=True)
     planner_case('planner_d1_nh5', 0, 5, 8)
+    # depth > 1 look-ahead with action clipping, through the one-line-patched copy of the reference planner
+    planner_tree_case('planner_d2w2_nh5', 0, 5, 6, 2, 2, speed_samples=2, rotation_samples=5)           # BASELINE C3: 11 actions
+    planner_tree_case('planner_d2w2_a81_nh5', 1, 5, 4, 2, 2)                                            # mp_separate_dp: 81 actions
+    planner_tree_case('planner_d3w2_nh5', 2, 5, 4, 3, 2, speed_samples=2, rotation_samples=5)
+    planner_tree_case('planner_d2w3_sparse_nh5', 0, 5, 4, 2, 3, sparse=True)                            # sparse search (:252-263)
 
 
 if __name__ == '__main__':

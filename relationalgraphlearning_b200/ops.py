@@ -27,6 +27,13 @@ def _f32c(t):
 
 
 # ---------------------------------------------------------------- weight packing ----------------
+def capturing():
+    """True while the current CUDA stream is being captured into a CUDA graph.  The TRAINING forwards then re-pack their
+    weights unconditionally: a captured optimizer step changes the parameters on every replay, but the host-side
+    (data_ptr, _version) check only runs at capture time -- the pack kernel has to be part of the graph."""
+    return torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+
+
 class _PackCache(object):
     """Packed k-major blob of one module, rebuilt when any parameter changed.
 
@@ -41,9 +48,9 @@ class _PackCache(object):
     def mark_dirty(self):
         self.key = None
 
-    def get(self, params, nfloats, pack_fn):
+    def get(self, params, nfloats, pack_fn, force=False):
         key = tuple((p.data_ptr(), p._version) for p in params)
-        if key != self.key or self.blob is None or self.blob.device != params[0].device:
+        if force or key != self.key or self.blob is None or self.blob.device != params[0].device:
             dev = params[0].device
             if self.blob is None or self.blob.device != dev or self.blob.numel() != nfloats:
                 self.blob = torch.empty(nfloats, dtype=torch.float32, device=dev)
@@ -59,7 +66,7 @@ def _graph_param_list(rgl):
             rgl.w_h[0].weight, rgl.w_h[0].bias, rgl.w_h[2].weight, rgl.w_h[2].bias, rgl.w_a] + list(rgl.Ws)
 
 
-def packed_graph(rgl):
+def packed_graph(rgl, force=False):
     params = _graph_param_list(rgl)          # (the cache key reads data_ptr / _version only: no detach() on the fast path)
     L = len(rgl.Ws)
     lib = _lib.lib()
@@ -75,10 +82,10 @@ def packed_graph(rgl):
         gp.num_layer = L
         _lib.check(lib.rgl_pack_graph(ctypes.byref(gp), _lib.ptr(blob), _lib.stream_ptr(blob.device)), 'rgl_pack_graph')
 
-    return rgl._pack_cache.get(params, int(lib.rgl_packed_graph_floats(L)), pack)
+    return rgl._pack_cache.get(params, int(lib.rgl_packed_graph_floats(L)), pack, force)
 
 
-def packed_value(seq, cache):
+def packed_value(seq, cache, force=False):
     params = [seq[0].weight, seq[0].bias, seq[2].weight, seq[2].bias, seq[4].weight, seq[4].bias,
               seq[6].weight, seq[6].bias]
     lib = _lib.lib()
@@ -90,10 +97,10 @@ def packed_value(seq, cache):
             setattr(vp, nme, t.data_ptr())
         _lib.check(lib.rgl_pack_value(ctypes.byref(vp), _lib.ptr(blob), _lib.stream_ptr(blob.device)), 'rgl_pack_value')
 
-    return cache.get(params, int(lib.rgl_packed_value_floats()), pack)
+    return cache.get(params, int(lib.rgl_packed_value_floats()), pack, force)
 
 
-def packed_motion(seq, cache):
+def packed_motion(seq, cache, force=False):
     params = [seq[0].weight, seq[0].bias, seq[2].weight, seq[2].bias]
     lib = _lib.lib()
 
@@ -104,7 +111,7 @@ def packed_motion(seq, cache):
             setattr(mp, nme, t.data_ptr())
         _lib.check(lib.rgl_pack_motion(ctypes.byref(mp), _lib.ptr(blob), _lib.stream_ptr(blob.device)), 'rgl_pack_motion')
 
-    return cache.get(params, int(lib.rgl_packed_motion_floats()), pack)
+    return cache.get(params, int(lib.rgl_packed_motion_floats()), pack, force)
 
 
 # ---------------------------------------------------------------- raw forward ops ----------------

@@ -69,7 +69,7 @@ def _graph_forward_train(g, robot, humans, extra_sizes, motion_blob=None, want_E
         cs.M[l], cs.Rl[l], cs.Hl[l] = sv['M'][l].data_ptr(), sv['Rl'][l].data_ptr(), sv['Hl'][l].data_ptr()
     cs.mh = sv['mh'].data_ptr() if want_S else None
     with torch.cuda.device(dev):
-        rc = _lib.lib().rgl_graph_forward_train(_lib.ptr(robot), _lib.ptr(humans), B, Nh, _lib.ptr(ops.packed_graph(g)), L, g.flags() & ~_lib.FLAG_FP32_FMA,
+        rc = _lib.lib().rgl_graph_forward_train(_lib.ptr(robot), _lib.ptr(humans), B, Nh, _lib.ptr(ops.packed_graph(g, force=ops.capturing())), L, g.flags() & ~_lib.FLAG_FP32_FMA,
                                                 _lib.ptr(motion_blob) if want_S else None, ctypes.byref(cs), None,
                                                 _lib.ptr(E), _lib.ptr(S), _lib.stream_ptr(dev))
     _lib.check(rc, 'rgl_graph_forward_train')
@@ -141,7 +141,7 @@ class _ValueTrain(torch.autograd.Function):
         sv, ex, E, _ = _graph_forward_train(g, robot, humans, [B, B * 32, B * 128, B * 128], want_E=True)
         V, v0, v1, v2 = ex[0].view(B, 1), ex[1].view(B, 32), ex[2].view(B, 128), ex[3].view(B, 128)
         with torch.cuda.device(dev):
-            rc = _lib.lib().rgl_value_head_train(_lib.ptr(E), B, _lib.ptr(ops.packed_value(ve.value_network, ve._pack_cache)),
+            rc = _lib.lib().rgl_value_head_train(_lib.ptr(E), B, _lib.ptr(ops.packed_value(ve.value_network, ve._pack_cache, force=ops.capturing())),
                                                  _lib.ptr(V), _lib.ptr(v0), _lib.ptr(v1), _lib.ptr(v2), _lib.stream_ptr(dev))
         _lib.check(rc, 'rgl_value_head_train')
         ops._count(1)
@@ -183,7 +183,7 @@ class _StatePredTrain(torch.autograd.Function):
     def forward(ctx, sp, detach, robot, humans, *params):
         g = sp.graph_model
         robot, humans = ops._check_state(robot, humans)
-        mblob = ops.packed_motion(sp.human_motion_predictor, sp._pack_cache)
+        mblob = ops.packed_motion(sp.human_motion_predictor, sp._pack_cache, force=ops.capturing())
         sv, _, _, S = _graph_forward_train(g, robot, humans, [], motion_blob=mblob, want_S=True)
         ctx.sp, ctx.sv, ctx.acts, ctx.detach = sp, sv, (robot, humans), detach
         return S.clone()

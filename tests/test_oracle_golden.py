@@ -109,3 +109,58 @@ def test_next_robot_state_matches_reference_rule():
     exp[2] = 0.3
     exp[3] = -0.7
     assert torch.equal(out.squeeze(), exp)
+
+
+TREE_CASES = ['planner_d2w2_nh5', 'planner_d2w2_a81_nh5', 'planner_d3w2_nh5', 'planner_d2w3_sparse_nh5']
+
+
+def tree_kw(g):
+    m = g['meta']
+    return dict(planning_depth=int(m[4]), planning_width=int(m[5]), do_action_clip=True, sparse_search=bool(m[6]),
+                speed_samples=int(m[7]), rotation_samples=int(m[8]))
+
+
+@pytest.mark.parametrize('case', TREE_CASES)
+def test_planner_depth_gt1_matches_patched_reference(case):
+    """Depth > 1 look-ahead with action clipping: the restated tree vs the reference planner run through the one-line patch
+    of oracle/make_ref.py (`values.append(float(value))`, model_predictive_rl.py:250).  Same kept action set at the root,
+    same per-action values (float32 look-ahead rewards under NEP-50 numpy: <= 1e-7), same chosen action."""
+    g = load_golden(case)
+    torch.set_num_threads(1)
+    pl = P.OraclePlanner(g['graph1'], g['value'], g['graph2'], g['motion'], **tree_kw(g))
+    for b in range(g['robot'].shape[0]):
+        a, v, table = pl.predict(g['robot'][b:b + 1], g['humans'][b:b + 1])
+        kept = [int(x) for x in g['kept'][b]]
+        assert sorted(table) == sorted(kept), (case, b)
+        ref = dict(zip(kept, np.asarray(g['values'][b], dtype=np.float64)))
+        for k in kept:
+            assert abs(table[k] - ref[k]) <= 1e-7, (case, b, k)
+        assert a == int(g['chosen'][b])
+        assert int(g['traj'][b][0]) == a
+
+
+def test_vendored_reference_modules_reproduce_the_goldens():
+    """oracle/_ref (oracle/make_ref.py: the reference's own modules, vendored unmodified; what bench.py's reference arm
+    times) reproduces the committed fixtures bit for bit -- the fixtures were minted from /root/reference itself."""
+    from oracle import make_ref
+    if not make_ref.enable():
+        pytest.skip('oracle/_ref not built (needs the reference checkout: python oracle/make_ref.py)')
+    from crowd_nav.configs.icra_benchmark.mp_separate import PolicyConfig
+    from crowd_nav.policy.graph_model import RGL
+    from crowd_nav.policy.state_predictor import StatePredictor
+    from crowd_nav.policy.value_estimator import ValueEstimator
+    for case in ('fwd_nh5_s0', 'fwd_nh20_s0'):
+        g = load_golden(case)
+        cfg = PolicyConfig()
+        g1 = RGL(cfg, 9, 5)
+        ve = ValueEstimator(cfg, g1)
+        g2 = RGL(cfg, 9, 5)
+        sp = StatePredictor(cfg, g2, 0.25)
+        g1.load_state_dict(g['graph1'])
+        ve.value_network.load_state_dict(g['value'])
+        g2.load_state_dict(g['graph2'])
+        sp.human_motion_predictor.load_state_dict(g['motion'])
+        with torch.no_grad():
+            assert torch.equal(g1((g['robot'], g['humans'])), g['H'])
+            assert torch.equal(ve((g['robot'], g['humans'])), g['V'])
+            assert torch.equal(sp((g['robot'], g['humans']), None)[1], g['S'])

@@ -169,6 +169,41 @@ def test_tree_planning_matches_oracle(cfg, cuda_device):
             assert abs(max(got.values()) - v) <= 1e-4, (cfg, b, got, table)
 
 
+TREE_CASES = ['planner_d2w2_nh5', 'planner_d2w2_a81_nh5', 'planner_d3w2_nh5', 'planner_d2w3_sparse_nh5']
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('case', TREE_CASES)
+@pytest.mark.parametrize('graphed', [False, True])
+def test_tree_planning_matches_patched_reference_golden(case, graphed, cuda_device):
+    """Depth > 1 pin: golden vectors minted by the reference planner itself (one-line patch, oracle/make_ref.py) --
+    kept action set after action_clip, value of every kept action, chosen action and the best trajectory's action
+    sequence (model_predictive_rl.py:212-233, 242-302)."""
+    g = load_golden(case)
+    m = g['meta']
+    pol = make_policy(g, cuda_device, planning_depth=int(m[4]), planning_width=int(m[5]), do_action_clip=True,
+                      sparse_search=bool(m[6]), speed_samples=int(m[7]), rotation_samples=int(m[8]))
+    pol.use_cuda_graphs = graphed
+    pol.build_action_space(1.0)
+    robot, humans = g['robot'].to(cuda_device), g['humans'].to(cuda_device)
+    best, det = pol.predict_batch(robot, humans, return_details=True)
+    for b in range(robot.size(0)):
+        kept = [int(x) for x in g['kept'][b]]
+        ref = dict(zip(kept, np.asarray(g['values'][b], dtype=np.float64)))
+        got = {int(det['acts'][b, k]): float(det['value'][b, k]) for k in range(det['acts'].size(1))}
+        srt = sorted(ref.values(), reverse=True)
+        assert set(got) == set(ref), (case, b, got, ref)
+        for k in kept:
+            assert abs(got[k] - ref[k]) <= 1e-5 * max(1.0, abs(ref[k])), (case, b, k, got[k], ref[k])
+        if srt[0] - srt[1] > 2e-5:
+            assert int(best[b]) == int(g['chosen'][b]), (case, b)
+            a = pol.predict(joint_state(g['robot'], g['humans'], b))
+            assert a == pol.action_space[int(g['chosen'][b])]
+            want = [int(x) for x in g['traj'][b] if x >= 0]
+            have = [pol.action_space.index(t[1]) for t in pol.get_traj() if t[1] is not None]
+            assert have == want, (case, b, have, want)
+
+
 @pytest.mark.gpu
 def test_batched_roots_equal_single_roots(cuda_device):
     g = load_golden('fwd_nh5_s0')
