@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define RGL_B200_VERSION 100          /* major*10000 + minor*100 + patch */
+#define RGL_B200_VERSION 200          /* major*10000 + minor*100 + patch */
 
 #define RGL_X_DIM        32           /* config.gcn.X_dim = final_state_dim (configs/icra_benchmark/config.py:103-108) */
 #define RGL_EMB_HIDDEN   64           /* wr_dims[0] = wh_dims[0] */
@@ -135,21 +135,39 @@ int rgl_gcn_layer(const float* X, const float* A, const float* W, const float* w
                   int B, int n, int flags, float* Hout, float* Aout, rgl_stream_t stream);
 
 /* ---- batched look-ahead step (planner inner loop) -------------------------------------------------
- * For every (state e, action a): next robot state (state_predictor.py:41-60, holonomic) and the
- * reward estimate (model_predictive_rl.py:304-357 + crowd_sim/envs/utils/utils.py:4-26), in one
- * launch.  actions: DEVICE double [A,2] = (vx, vy) (model_predictive_rl.py:155-190 builds them in
- * float64).  Outputs: next_robot [E*A,1,9] fp32 (row e*A+a), reward [E*A] fp32.  State e reads
- * humans[e / humans_bcast] (look-ahead children of one parent share its predicted humans).
- * Reward arithmetic is float64 on the fp32 state values. */
+ * For every (state e, action a): next robot state (state_predictor.py:41-60) and the reward estimate
+ * (model_predictive_rl.py:304-357 + crowd_sim/envs/utils/utils.py:4-26), in one launch.
+ * actions: DEVICE double [A,2] (model_predictive_rl.py:155-190 builds them in float64):
+ *   RGL_KIN_HOLONOMIC (vx, vy)  ActionXY;   RGL_KIN_UNICYCLE (v, r)  ActionRot -- the next-state rule keeps the
+ *   reference's indexing (the rotation is added to element 7 of the robot state, state_predictor.py:54).
+ * Outputs: next_robot [E*A,1,9] fp32 (row e*A+a), reward [E*A] fp32.  State e reads humans[e / humans_bcast]
+ * (look-ahead children of one parent share its predicted humans).  Reward arithmetic is float64 on the fp32 state values. */
+#define RGL_KIN_HOLONOMIC 0
+#define RGL_KIN_UNICYCLE  1
 int rgl_plan_expand(const float* robot, const float* humans, int E, int Nh, int humans_bcast,
-                    const double* actions, int A, double time_step,
+                    const double* actions, int A, double time_step, int kinematics,
                     float* next_robot, float* reward, rgl_stream_t stream);
 
 /* value[e,a] = reward[e,a] + gamma_bar * V[e*A+a] (fp32, same op order as model_predictive_rl.py:227);
- * best[e] = first index of the maximum (strict '>' scan, model_predictive_rl.py:228-231),
- * -1 if every value is NaN/-inf. */
+ * best[e] = first index of the maximum (strict '>' scan, model_predictive_rl.py:228-231), -1 if every value is NaN/-inf.
+ * act_map (optional, DEVICE int32 [E,A]): the action each column stands for after action clipping;
+ * best_action[e] = act_map[e,best[e]] (= best[e] without a map). */
 int rgl_plan_argmax(const float* reward, const float* V, int E, int A, float gamma_bar,
-                    float* value, int* best, rgl_stream_t stream);
+                    float* value, int* best, const int* act_map, int* best_action, rgl_stream_t stream);
+
+/* action_clip (model_predictive_rl.py:242-269) for E states at once: value = reward + gamma_bar * V as above, then the
+ * `width` best actions per state -> acts [E,width] int32.  groups == NULL: descending value, ties by lower index;
+ * groups (DEVICE int32 [A], action_group_index :168-181): sparse search (:252-263).  Also gathers what the next tree
+ * level reads: child_reward [E,width] = reward[e,acts], child_robot [E*width,1,9] = next_robot[e*A+acts] (both optional);
+ * value [E,A] optional. */
+int rgl_plan_select(const float* reward, const float* V, int E, int A, float gamma_bar, int width, const int* groups,
+                    const float* next_robot, int* acts, float* child_reward, float* child_robot, float* value,
+                    rgl_stream_t stream);
+
+/* V_planning backup (model_predictive_rl.py:293-298): ret[e,k] = v[e]/depth + (depth-1)/depth * (gamma_bar*next_v[e,k] + reward[e,k])
+ * (fp32, every operation rounded as in the reference's tensor expression); ret_best[e] = max_k, best[e] = first argmax. */
+int rgl_plan_backup(const float* v, const float* next_v, const float* reward, int E, int W, float gamma_bar, int depth,
+                    float* ret_best, int* best, rgl_stream_t stream);
 
 
 /* ---- training step (value estimator): forward with activation saves + backward building blocks -----------------

@@ -106,12 +106,13 @@ def stub_sim_deps():
     sys.modules['matplotlib.collections'].PatchCollection = object
 
 
-def planner_case(name, seed, nh, n_states, data_seed=77):
+def planner_case(name, seed, nh, n_states, data_seed=77, kinematics='holonomic'):
     """Depth-1 predict() of the unmodified reference planner on n_states synthetic JointStates."""
     stub_sim_deps()
     from crowd_nav.policy.model_predictive_rl import ModelPredictiveRL
     from crowd_sim.envs.utils.state import FullState, ObservableState, JointState
     cfg = load_ref_config('mp_separate').PolicyConfig()
+    cfg.action_space.kinematics = kinematics
     torch.manual_seed(seed)
     pol = ModelPredictiveRL()
     pol.configure(cfg)
@@ -142,7 +143,7 @@ def planner_case(name, seed, nh, n_states, data_seed=77):
                 vals.append(float(rew + pol.get_normalized_gamma() * v))
             values.append(vals); rewards.append(rews); vnext.append(vns)
             # look-ahead style reward: state given as a tensor tuple (tensor_to_joint_state path)
-    actions = np.array([[a.vx, a.vy] for a in pol.action_space], dtype=np.float64)
+    actions = np.array([[a[0], a[1]] for a in pol.action_space], dtype=np.float64)     # (vx, vy) or, unicycle, (v, r)
     sd = pol.get_state_dict()
     out = {}
     out.update(sd_np(sd['graph_model1'], 'graph1/'))
@@ -245,6 +246,7 @@ def main():
     forward_case('fwd_nh5_layerwise_noskip', 0, 5, 64, layerwise=True, skip=False)   # BasePolicyConfig defaults
     forward_case('fwd_nh5_layerwise_skip', 1, 5, 64, layerwise=True, skip=True)
     planner_case('planner_d1_nh5', 0, 5, 8)
+    planner_case('planner_d1_unicycle_nh5', 1, 5, 6, data_seed=78, kinematics='unicycle')     # ActionRot branch (:204,:319-321,:337-340)
     # depth > 1 look-ahead with action clipping, through the one-line-patched copy of the reference planner
     planner_tree_case('planner_d2w2_nh5', 0, 5, 6, 2, 2, speed_samples=2, rotation_samples=5)           # BASELINE C3: 11 actions
     planner_tree_case('planner_d2w2_a81_nh5', 1, 5, 4, 2, 2)                                            # mp_separate_dp: 81 actions

@@ -34,19 +34,21 @@ from oracle import rgl_oracle as O
 
 
 def build_action_space(v_pref, speed_samples=5, rotation_samples=16, kinematics='holonomic',
-                       sparse_rotation_samples=8):
-    """Returns (actions float64 [A,2] = (vx, vy), action_group_index list) in speed-major order."""
-    if kinematics != 'holonomic':
-        raise NotImplementedError
+                       sparse_rotation_samples=8, rotation_constraint=np.pi / 3):
+    """Returns (actions float64 [A,2] = (vx, vy) holonomic | (v, r) unicycle, action_group_index list), speed-major."""
+    holonomic = kinematics == 'holonomic'
     speeds = [(np.exp((i + 1) / speed_samples) - 1) / (np.e - 1) * v_pref for i in range(speed_samples)]
-    rotations = np.linspace(0, 2 * np.pi, rotation_samples, endpoint=False)
+    if holonomic:
+        rotations = np.linspace(0, 2 * np.pi, rotation_samples, endpoint=False)
+    else:
+        rotations = np.linspace(-rotation_constraint, rotation_constraint, rotation_samples)
     actions = [(0.0, 0.0)]
     groups = [0]
     for j, speed in enumerate(speeds):
         sg = 0 if j < 3 else 1
         for i, rot in enumerate(rotations):
             groups.append(sg * sparse_rotation_samples + i // 2)
-            actions.append((speed * np.cos(rot), speed * np.sin(rot)))
+            actions.append((speed * np.cos(rot), speed * np.sin(rot)) if holonomic else (speed, rot))
     return np.asarray(actions, dtype=np.float64), groups
 
 
@@ -65,10 +67,14 @@ def point_to_segment_dist(x1, y1, x2, y2, x3, y3):
     return float(np.linalg.norm((x - x3, y - y3)))   # same library call as utils.py:26 (dot + sqrt)
 
 
-def estimate_reward(robot, humans, action, time_step):
-    """robot: 9 floats, humans: [Nh][5] floats, action (vx, vy).  Returns python float."""
+def estimate_reward(robot, humans, action, time_step, kinematics='holonomic'):
+    """robot: 9 floats, humans: [Nh][5] floats, action (vx, vy) | unicycle (v, r).  Returns python float."""
     rpx, rpy, _, _, rrad, gx, gy = [float(v) for v in robot[:7]]
-    avx, avy = float(action[0]), float(action[1])
+    if kinematics == 'holonomic':
+        avx, avy = float(action[0]), float(action[1])
+    else:       # model_predictive_rl.py:319-321,337-340: heading = action.r + theta (theta = element 8)
+        th = float(action[1]) + float(robot[8])
+        avx, avy = float(action[0]) * np.cos(th), float(action[0]) * np.sin(th)
     dmin = float('inf')
     collision = False
     for h in humans:
@@ -102,14 +108,15 @@ class OraclePlanner(object):
 
     def __init__(self, graph_sd_v, value_sd, graph_sd_s, motion_sd, gamma=0.9, time_step=0.25, v_pref=1.0,
                  planning_depth=1, planning_width=1, do_action_clip=False, sparse_search=False,
-                 speed_samples=5, rotation_samples=16, linear_state_predictor=False, graph_kw=None):
+                 speed_samples=5, rotation_samples=16, linear_state_predictor=False, graph_kw=None, kinematics='holonomic'):
         self.gv, self.vn, self.gs, self.mp = graph_sd_v, value_sd, graph_sd_s, motion_sd
         self.gamma, self.time_step, self.v_pref = gamma, time_step, v_pref
         self.depth, self.width = planning_depth, planning_width
         self.do_action_clip, self.sparse_search = do_action_clip, sparse_search
         self.linear = linear_state_predictor
         self.graph_kw = graph_kw or {}
-        self.actions, self.groups = build_action_space(v_pref, speed_samples, rotation_samples)
+        self.kinematics = kinematics
+        self.actions, self.groups = build_action_space(v_pref, speed_samples, rotation_samples, kinematics)
         self.n_value_fwd = 0
         self.n_sp_fwd = 0
 
@@ -126,7 +133,7 @@ class OraclePlanner(object):
         self.n_sp_fwd += 1
         vx, vy = self.actions[a]
         with torch.no_grad():
-            nr = O.next_robot_state(state[0], vx, vy, self.time_step)
+            nr = O.next_robot_state(state[0], vx, vy, self.time_step, self.kinematics)
             if self.linear:
                 nh = O.linear_motion(state[1])
             else:
@@ -136,7 +143,7 @@ class OraclePlanner(object):
     def R(self, state, a):
         robot = state[0].reshape(-1).numpy().astype(np.float64)
         humans = state[1].reshape(-1, 5).numpy().astype(np.float64)
-        return estimate_reward(robot, humans, self.actions[a], self.time_step)
+        return estimate_reward(robot, humans, self.actions[a], self.time_step, self.kinematics)
 
     # --- tree -------------------------------------------------------------------------------
     def action_clip(self, state, width):

@@ -118,8 +118,7 @@ def next_robot_state(robot, vx, vy, time_step, kinematics='holonomic'):
     fp32 tensor + python-scalar add, i.e. fp32(p) + fp32(a*dt) rounded to fp32.
     """
     if kinematics != 'holonomic':
-        raise NotImplementedError('only the holonomic branch is configured (config.py:69); the '
-                                  'unicycle branch of the reference indexes v_pref as heading (SURVEY.md §5)')
+        return next_robot_state_unicycle(robot, vx, vy, time_step)
     out = robot.clone()
     dt = float(time_step)
     vx = torch.as_tensor(vx, dtype=torch.float64)
@@ -129,6 +128,23 @@ def next_robot_state(robot, vx, vy, time_step, kinematics='holonomic'):
     out[:, 0, 2] = vx.to(robot.dtype)
     out[:, 0, 3] = vy.to(robot.dtype)
     return out
+
+
+def next_robot_state_unicycle(robot, v, r, time_step):
+    """Unicycle branch of state_predictor.py:53-58 for robot[1,1,9], ActionRot (v, r) as python floats.
+
+    The reference adds the rotation to element 7 (v_pref; the heading is element 8 -- SURVEY.md 5; kept), then
+    `np.cos(next_state[7]) * action.v * self.time_step`: np.cos of a 0-dim fp32 tensor comes back as a 0-dim fp32
+    TENSOR (Tensor.__array_wrap__), so the products are fp32 tensor-times-python-scalar operations."""
+    import numpy as np
+    assert robot.shape[0] == 1
+    out = robot.clone().squeeze()
+    out[7] = out[7] + float(r)
+    out[0] = out[0] + np.cos(out[7]) * float(v) * float(time_step)
+    out[1] = out[1] + np.sin(out[7]) * float(v) * float(time_step)
+    out[2] = np.cos(out[7]) * float(v)
+    out[3] = np.sin(out[7]) * float(v)
+    return out.unsqueeze(0).unsqueeze(0)
 
 
 def linear_motion(humans):

@@ -16,6 +16,8 @@ FLAG_SKIP = 1
 FLAG_LAYERWISE = 2
 FLAG_THROUGHPUT = 4
 FLAG_FP32_FMA = 8
+KIN_HOLONOMIC = 0
+KIN_UNICYCLE = 1
 
 c_float_p = ctypes.c_void_p
 
@@ -75,8 +77,12 @@ EXPORTS = {
     'rgl_sim_bwd': (ctypes.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, ctypes.c_int, ctypes.c_int,
                                    ctypes.c_void_p]),
     'rgl_plan_expand': (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
-                                       ctypes.c_int, ctypes.c_double, c_float_p, c_float_p, ctypes.c_void_p]),
+                                       ctypes.c_int, ctypes.c_double, ctypes.c_int, c_float_p, c_float_p, ctypes.c_void_p]),
     'rgl_plan_argmax': (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                       c_float_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    'rgl_plan_select': (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int,
+                                       ctypes.c_void_p, c_float_p, ctypes.c_void_p, c_float_p, c_float_p, c_float_p, ctypes.c_void_p]),
+    'rgl_plan_backup': (ctypes.c_int, [c_float_p, c_float_p, c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int,
                                        c_float_p, ctypes.c_void_p, ctypes.c_void_p]),
     # data-parallel gradient exchange over NVLink peer memory (csrc/dp_comm.cu)
     'rgl_comm_create': (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_longlong, ctypes.POINTER(ctypes.c_void_p)]),

@@ -151,25 +151,45 @@ int rgl_gcn_layer(const float* X, const float* A, const float* W, const float* w
 }
 
 int rgl_plan_expand(const float* robot, const float* humans, int E, int Nh, int humans_bcast, const double* actions, int A,
-                    double time_step,
+                    double time_step, int kinematics,
                     float* next_robot, float* reward, rgl_stream_t stream) {
     if (E == 0) return RGL_OK;
     if (!robot || !actions || E < 0 || A < 1 || Nh < 0 || humans_bcast < 1) return fail(RGL_EINVAL, "rgl_plan_expand: bad argument");
+    if (kinematics != RGL_KIN_HOLONOMIC && kinematics != RGL_KIN_UNICYCLE) return fail(RGL_EINVAL, "rgl_plan_expand: unknown kinematics");
     if (reward && Nh > 0 && !humans) return fail(RGL_EINVAL, "rgl_plan_expand: reward needs humans");
     if (!next_robot && !reward) return fail(RGL_EINVAL, "rgl_plan_expand: no output requested");
     if ((long long)E * A > 0x7fffffffLL) return fail(RGL_EUNSUPPORTED, "rgl_plan_expand: E*A too large");
-    if (E == 0) return RGL_OK;
-    cudaError_t e = rgl::run_plan_expand(robot, humans, E, Nh, humans_bcast, actions, A, time_step, next_robot, reward, (cudaStream_t)stream);
+    cudaError_t e = rgl::run_plan_expand(robot, humans, E, Nh, humans_bcast, actions, A, time_step, kinematics == RGL_KIN_UNICYCLE,
+                                         next_robot, reward, (cudaStream_t)stream);
     return e == cudaSuccess ? RGL_OK : fail_cuda(e, "rgl_plan_expand");
 }
 
 int rgl_plan_argmax(const float* reward, const float* V, int E, int A, float gamma_bar, float* value, int* best,
+                    const int* act_map, int* best_action, rgl_stream_t stream) {
+    if (E == 0) return RGL_OK;
+    if (!reward || !V || E < 0 || A < 1 || (!value && !best && !best_action)) return fail(RGL_EINVAL, "rgl_plan_argmax: bad argument");
+    cudaError_t e = rgl::run_plan_argmax(reward, V, E, A, gamma_bar, value, best, act_map, best_action, (cudaStream_t)stream);
+    return e == cudaSuccess ? RGL_OK : fail_cuda(e, "rgl_plan_argmax");
+}
+
+int rgl_plan_select(const float* reward, const float* V, int E, int A, float gamma_bar, int width, const int* groups,
+                    const float* next_robot, int* acts, float* child_reward, float* child_robot, float* value,
                     rgl_stream_t stream) {
     if (E == 0) return RGL_OK;
-    if (!reward || !V || E < 0 || A < 1 || (!value && !best)) return fail(RGL_EINVAL, "rgl_plan_argmax: bad argument");
+    if (!reward || !V || !acts || E < 0 || A < 1 || width < 1 || width > A) return fail(RGL_EINVAL, "rgl_plan_select: bad argument");
+    if (child_robot && !next_robot) return fail(RGL_EINVAL, "rgl_plan_select: child_robot needs next_robot");
+    if (A > 256) return fail(RGL_EUNSUPPORTED, "rgl_plan_select: more than 256 actions");
+    cudaError_t e = rgl::run_plan_select(reward, V, E, A, gamma_bar, width, groups, next_robot, acts, child_reward, child_robot, value,
+                                         (cudaStream_t)stream);
+    return e == cudaSuccess ? RGL_OK : fail_cuda(e, "rgl_plan_select");
+}
+
+int rgl_plan_backup(const float* v, const float* next_v, const float* reward, int E, int W, float gamma_bar, int depth,
+                    float* ret_best, int* best, rgl_stream_t stream) {
     if (E == 0) return RGL_OK;
-    cudaError_t e = rgl::run_plan_argmax(reward, V, E, A, gamma_bar, value, best, (cudaStream_t)stream);
-    return e == cudaSuccess ? RGL_OK : fail_cuda(e, "rgl_plan_argmax");
+    if (!v || !next_v || !reward || !ret_best || !best || E < 0 || W < 1 || depth < 2) return fail(RGL_EINVAL, "rgl_plan_backup: bad argument");
+    cudaError_t e = rgl::run_plan_backup(v, next_v, reward, E, W, gamma_bar, depth, ret_best, best, (cudaStream_t)stream);
+    return e == cudaSuccess ? RGL_OK : fail_cuda(e, "rgl_plan_backup");
 }
 
 int rgl_graph_forward_train(const float* robot, const float* humans, int B, int Nh, const float* graph_packed, int num_layer,

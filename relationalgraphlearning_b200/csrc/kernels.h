@@ -70,8 +70,12 @@ cudaError_t run_pack_graph(const RglGraphParams& p, float* out, cudaStream_t st)
 cudaError_t run_pack_value(const RglValueParams& p, float* out, cudaStream_t st);
 cudaError_t run_pack_motion(const RglMotionParams& p, float* out, cudaStream_t st);
 cudaError_t run_plan_expand(const float* robot, const float* humans, int E, int Nh, int hb, const double* actions, int A, double dt,
-                            float* next_robot, float* reward, cudaStream_t st);
+                            int unicycle, float* next_robot, float* reward, cudaStream_t st);
 cudaError_t run_plan_argmax(const float* reward, const float* V, int E, int A, float gamma_bar, float* value, int* best,
-                            cudaStream_t st);
+                            const int* act_map, int* best_action, cudaStream_t st);
+cudaError_t run_plan_select(const float* reward, const float* V, int E, int A, float gamma_bar, int width, const int* groups,
+                            const float* next_robot, int* acts, float* child_rew, float* child_robot, float* value, cudaStream_t st);
+cudaError_t run_plan_backup(const float* v, const float* nv, const float* rew, int E, int W, float gamma_bar, int depth,
+                            float* ret_best, int* best, cudaStream_t st);
 
 }  // namespace rgl

@@ -122,27 +122,48 @@ __global__ void pack_motion_kernel(RglMotionParams p, float* out) {
 }
 
 // ---- planner: one thread per (state e, action a) ------------------------------------------------------
-// next robot state: crowd_nav/policy/state_predictor.py:48-52 (fp32 position + fp32(v*dt), velocity = action)
+// next robot state: crowd_nav/policy/state_predictor.py:48-52 (holonomic: fp32 position + fp32(v*dt), velocity = action)
+//                   and :53-58 (unicycle: the rotation is added to element 7 exactly as the reference does -- element 7
+//                   is v_pref, the heading is element 8; SURVEY.md 5 -- then cos / sin of that element steer the step)
 // reward:           crowd_nav/policy/model_predictive_rl.py:304-357, crowd_sim/envs/utils/utils.py:4-26, in float64
+// actions: (vx, vy) holonomic | (v, r) unicycle
 __global__ void plan_expand_kernel(const float* __restrict__ robot, const float* __restrict__ humans, int E, int Nh, int hb,
-                                   const double* __restrict__ actions, int A, double dt,
+                                   const double* __restrict__ actions, int A, double dt, int unicycle,
                                    float* __restrict__ next_robot, float* __restrict__ reward) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= E * A) return;
     const int e = idx / A, a = idx - e * A;
     const float* r = robot + (size_t)e * RD;
-    const double avx = actions[2 * a], avy = actions[2 * a + 1];
+    const double a0 = actions[2 * a], a1 = actions[2 * a + 1];
     if (next_robot) {
         float* o = next_robot + (size_t)idx * RD;
-        o[0] = __fadd_rn(r[0], (float)(avx * dt));
-        o[1] = __fadd_rn(r[1], (float)(avy * dt));
-        o[2] = (float)avx;
-        o[3] = (float)avy;
 #pragma unroll
         for (int c = 4; c < RD; ++c) o[c] = r[c];
+        if (!unicycle) {
+            o[0] = __fadd_rn(r[0], (float)(a0 * dt));
+            o[1] = __fadd_rn(r[1], (float)(a1 * dt));
+            o[2] = (float)a0;
+            o[3] = (float)a1;
+        } else {
+            const float h7 = __fadd_rn(r[7], (float)a1);
+            const float c = cosf(h7), sn = sinf(h7);
+            const float cv = __fmul_rn(c, (float)a0), sv = __fmul_rn(sn, (float)a0);
+            o[7] = h7;
+            o[0] = __fadd_rn(r[0], __fmul_rn(cv, (float)dt));
+            o[1] = __fadd_rn(r[1], __fmul_rn(sv, (float)dt));
+            o[2] = cv;
+            o[3] = sv;
+        }
     }
     if (reward) {
         const double rpx = r[0], rpy = r[1], rrad = r[4], gx = r[5], gy = r[6];
+        // velocity of the robot under this action, world frame (unicycle: heading = theta + r, model_predictive_rl.py:319-321,337-340)
+        double avx = a0, avy = a1;
+        if (unicycle) {
+            const double th = __dadd_rn(a1, (double)r[8]);
+            avx = __dmul_rn(a0, cos(th));
+            avy = __dmul_rn(a0, sin(th));
+        }
         double dmin = INFINITY;
         bool collision = false;
         const float* h = humans + (size_t)(e / hb) * Nh * HD;
@@ -178,8 +199,11 @@ __global__ void plan_expand_kernel(const float* __restrict__ robot, const float*
 
 // value = fp32(reward) + fp32(gamma_bar) * V (two rounded fp32 ops, like the tensor expression in
 // model_predictive_rl.py:227); best = first index of the maximum under a strict '>' scan (:228-231).
+// act_map (optional, [E,A] int32): the actions the A columns stand for (after action clipping); best_action[e] =
+// act_map[e, best[e]] (or best[e] without a map; -1 if no finite value).
 __global__ void plan_argmax_kernel(const float* __restrict__ reward, const float* __restrict__ V, int E, int A, float gamma_bar,
-                                   float* __restrict__ value, int* __restrict__ best) {
+                                   float* __restrict__ value, int* __restrict__ best, const int* __restrict__ act_map,
+                                   int* __restrict__ best_action) {
     const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (e >= E) return;
@@ -196,7 +220,107 @@ __global__ void plan_argmax_kernel(const float* __restrict__ reward, const float
         const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
         if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
     }
-    if (lane == 0 && best) best[e] = bi;
+    if (lane == 0) {
+        if (best) best[e] = bi;
+        if (best_action) best_action[e] = (bi >= 0 && act_map) ? act_map[(size_t)e * A + bi] : bi;
+    }
+}
+
+// action_clip (model_predictive_rl.py:242-269) for one state per warp: value[a] = reward + gamma_bar * V (as above), then
+// the `width` best actions --
+//   groups == nullptr : descending value, ties by LOWER action index (the reference's argpartition order is unspecified;
+//                       oracle/planner_oracle.py pins this one);
+//   groups given      : sparse search (:252-263): walk by descending value, ties by HIGHER index (argsort()[::-1]), keep
+//                       the first action of every not-yet-seen group.
+// NaN values are never selected before any finite / infinite one.  Besides the kept indices acts[e,k] the kernel gathers
+// what the next tree level consumes: child_rew[e,k] = reward[e,acts] and child_robot[e*width+k] = next_robot[e*A+acts].
+constexpr int SEL_MAX_PER_LANE = 8;      // A <= 256
+__global__ void plan_select_kernel(const float* __restrict__ reward, const float* __restrict__ V, int E, int A, float gamma_bar,
+                                   int width, const int* __restrict__ groups, const float* __restrict__ next_robot,
+                                   int* __restrict__ acts, float* __restrict__ child_rew, float* __restrict__ child_robot,
+                                   float* __restrict__ value) {
+    const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (e >= E) return;
+    float v[SEL_MAX_PER_LANE];
+    unsigned taken = 0;                   // bit i: this lane's i-th action is no longer a candidate
+#pragma unroll
+    for (int i = 0; i < SEL_MAX_PER_LANE; ++i) {
+        const int a = lane + 32 * i;
+        v[i] = -INFINITY;
+        if (a < A) {
+            v[i] = __fadd_rn(reward[(size_t)e * A + a], __fmul_rn(gamma_bar, V[(size_t)e * A + a]));
+            if (value) value[(size_t)e * A + a] = v[i];
+        } else {
+            taken |= 1u << i;
+        }
+    }
+    for (int k = 0; k < width; ++k) {
+        // this lane's best remaining candidate (NaN ranks below everything)
+        float bv = 0.f;
+        int bi = -1;
+        bool bnan = true;
+#pragma unroll
+        for (int i = 0; i < SEL_MAX_PER_LANE; ++i) {
+            if (taken >> i & 1u) continue;
+            const int a = lane + 32 * i;
+            const bool isn = v[i] != v[i];
+            bool better;
+            if (bi < 0) better = true;
+            else if (isn != bnan) better = bnan;                                   // finite beats NaN
+            else if (isn) better = groups ? a > bi : a < bi;
+            else better = v[i] > bv || (v[i] == bv && (groups ? a > bi : a < bi));
+            if (better) { bv = v[i]; bi = a; bnan = isn; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            const bool on = __shfl_xor_sync(0xffffffffu, (int)bnan, off) != 0;
+            bool better;
+            if (oi < 0) better = false;
+            else if (bi < 0) better = true;
+            else if (on != bnan) better = bnan;
+            else if (on) better = groups ? oi > bi : oi < bi;
+            else better = ov > bv || (ov == bv && (groups ? oi > bi : oi < bi));
+            if (better) { bv = ov; bi = oi; bnan = on; }
+        }
+        // bi is warp-uniform now (every lane applied the same total order); -1 only if fewer candidates than width remain
+        if (bi >= 0) {
+            const int g = groups ? groups[bi] : 0;
+#pragma unroll
+            for (int i = 0; i < SEL_MAX_PER_LANE; ++i) {
+                const int a = lane + 32 * i;
+                if (a == bi || (groups && a < A && groups[a] == g)) taken |= 1u << i;
+            }
+        }
+        const int sel = bi < 0 ? 0 : bi;
+        if (lane == 0) {
+            acts[(size_t)e * width + k] = sel;
+            if (child_rew) child_rew[(size_t)e * width + k] = reward[(size_t)e * A + sel];
+        }
+        if (child_robot && lane < RD)
+            child_robot[((size_t)e * width + k) * RD + lane] = next_robot[((size_t)e * A + sel) * RD + lane];
+    }
+}
+
+// V_planning backup (model_predictive_rl.py:293,298): ret[e,k] = v[e] / depth + (depth-1)/depth * (gamma_bar * nv[e,k] + rew[e,k])
+// evaluated as the reference's fp32 tensor expression (every operation rounded separately); best = first maximum.
+__global__ void plan_backup_kernel(const float* __restrict__ v, const float* __restrict__ nv, const float* __restrict__ rew, int E,
+                                   int W, float gamma_bar, float depth, float frac, float* __restrict__ ret_best,
+                                   int* __restrict__ best) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    const float base = __fdiv_rn(v[e], depth);
+    float bv = 0.f;
+    int bi = -1;
+    for (int k = 0; k < W; ++k) {
+        const float t = __fadd_rn(__fmul_rn(gamma_bar, nv[(size_t)e * W + k]), rew[(size_t)e * W + k]);
+        const float r = __fadd_rn(base, __fmul_rn(frac, t));
+        if (bi < 0 || (bv == bv && (r > bv || r != r))) { bv = r; bi = k; }     // np.argmax: first maximum, a NaN counts as the maximum
+    }
+    ret_best[e] = bv;
+    best[e] = bi;
 }
 
 cudaError_t run_pack_graph(const RglGraphParams& p, float* out, cudaStream_t st) {
@@ -212,14 +336,26 @@ cudaError_t run_pack_motion(const RglMotionParams& p, float* out, cudaStream_t s
     return cudaGetLastError();
 }
 cudaError_t run_plan_expand(const float* robot, const float* humans, int E, int Nh, int hb, const double* actions, int A, double dt,
-                            float* next_robot, float* reward, cudaStream_t st) {
+                            int unicycle, float* next_robot, float* reward, cudaStream_t st) {
     const int total = E * A;
-    plan_expand_kernel<<<(total + 127) / 128, 128, 0, st>>>(robot, humans, E, Nh, hb, actions, A, dt, next_robot, reward);
+    plan_expand_kernel<<<(total + 127) / 128, 128, 0, st>>>(robot, humans, E, Nh, hb, actions, A, dt, unicycle, next_robot, reward);
     return cudaGetLastError();
 }
 cudaError_t run_plan_argmax(const float* reward, const float* V, int E, int A, float gamma_bar, float* value, int* best,
-                            cudaStream_t st) {
-    plan_argmax_kernel<<<(E + 3) / 4, 128, 0, st>>>(reward, V, E, A, gamma_bar, value, best);
+                            const int* act_map, int* best_action, cudaStream_t st) {
+    plan_argmax_kernel<<<(E + 3) / 4, 128, 0, st>>>(reward, V, E, A, gamma_bar, value, best, act_map, best_action);
+    return cudaGetLastError();
+}
+cudaError_t run_plan_select(const float* reward, const float* V, int E, int A, float gamma_bar, int width, const int* groups,
+                            const float* next_robot, int* acts, float* child_rew, float* child_robot, float* value, cudaStream_t st) {
+    if (A > 32 * SEL_MAX_PER_LANE) return cudaErrorInvalidConfiguration;
+    plan_select_kernel<<<(E + 3) / 4, 128, 0, st>>>(reward, V, E, A, gamma_bar, width, groups, next_robot, acts, child_rew, child_robot, value);
+    return cudaGetLastError();
+}
+cudaError_t run_plan_backup(const float* v, const float* nv, const float* rew, int E, int W, float gamma_bar, int depth,
+                            float* ret_best, int* best, cudaStream_t st) {
+    const float frac = (float)((double)(depth - 1) / (double)depth);
+    plan_backup_kernel<<<(E + 127) / 128, 128, 0, st>>>(v, nv, rew, E, W, gamma_bar, (float)depth, frac, ret_best, best);
     return cudaGetLastError();
 }
 

@@ -16,9 +16,11 @@ and the same per tree level for depth > 1 (action_clip + recursion, :242-302), f
 states at once (`predict_batch`).  Depth-1 planning = 5 launches instead of 162 module forwards.
 
 Deviations, all documented in DESIGN.md: the reference planner does not run at depth > 1 on current
-torch/numpy; the intended semantics implemented here are those restated (and tested) in
-oracle/planner_oracle.py: top-`width` by value with ties broken by lower action index, first-maximum
-argmax.  Look-ahead rewards are evaluated in float64 on the fp32 state values.
+torch/numpy without a one-line change (`float(value)` at :250, oracle/make_ref.py); the
+semantics implemented here -- top-`width` by value with ties broken by lower action index, first-maximum
+argmax -- are pinned by golden vectors minted from that patched reference (tests/golden/planner_d*).
+Look-ahead rewards are evaluated in float64 on the fp32 state values.  Both kinematics are implemented
+(ActionXY holonomic, ActionRot unicycle).
 """
 import logging
 
@@ -102,6 +104,8 @@ class ModelPredictiveRL(Policy):
             self.model = [graph_model1, graph_model2, self.value_estimator.value_network,
                           self.state_predictor.human_motion_predictor]
 
+        self._graphs = {}                      # captured look-aheads are bound to the previous modules' weight blobs
+        self._actions_dev = None
         logging.info('Planning depth: {}'.format(self.planning_depth))
         logging.info('Planning width: {}'.format(self.planning_width))
         logging.info('Sparse search: {}'.format(self.sparse_search))
@@ -197,12 +201,11 @@ class ModelPredictiveRL(Policy):
         self._actions_dev = None
 
     def _action_table(self):
+        """Device copy of the action table, float64 [A,2]: (vx, vy) holonomic | (v, r) unicycle (ActionRot)."""
         if self._actions_dev is None or self._actions_dev.device != torch.device(self.device):
-            if self.kinematics != 'holonomic':
-                raise NotImplementedError('batched planning implements the holonomic action space (config.py:69)')
-            tab = np.array([[a.vx, a.vy] for a in self.action_space], dtype=np.float64)
+            tab = np.array([[a[0], a[1]] for a in self.action_space], dtype=np.float64)
             self._actions_dev = torch.from_numpy(tab).to(self.device)
-            self._groups_dev = torch.tensor(self.action_group_index, dtype=torch.long, device=self.device)
+            self._groups_dev = torch.tensor(self.action_group_index, dtype=torch.int32, device=self.device)
             self._num_groups = max(self.action_group_index) + 1
             self._graphs = {}
         return self._actions_dev
@@ -211,7 +214,7 @@ class ModelPredictiveRL(Policy):
     def _expand(self, robot, humans, hb):
         """All actions of every state: (next_robot[N*A,1,9], reward[N,A]) in one launch."""
         acts = self._action_table()
-        nxt, rew = ops.plan_expand(robot, humans, acts, self.time_step, humans_bcast=hb)
+        nxt, rew = ops.plan_expand(robot, humans, acts, self.time_step, humans_bcast=hb, kinematics=self.kinematics)
         return nxt, rew.view(robot.size(0), acts.size(0))
 
     def _next_humans(self, robot, humans, hb):
@@ -226,28 +229,20 @@ class ModelPredictiveRL(Policy):
         self.stat_value_states += robot.size(0)
         return self.value_estimator.run(robot, humans, humans_bcast=hb).view(-1)
 
-    def _clip(self, robot, humans, hb, width):
-        """action_clip (:242-269) for N states at once -> (kept action indices [N,width], nxt, rew, nh)."""
+    def _clip(self, robot, humans, hb, width, want_value=False):
+        """action_clip (:242-269) for N states at once: 5 launches (state predictor, expand, graph + value head over the
+        N*A children, select).  -> dict(acts[N,width] int32, rew[N,width], robot[N*width,1,9], nh, all_rew[N,A], nxt, value)."""
         N, A = robot.size(0), len(self.action_space)
         nh = self._next_humans(robot, humans, hb)
         nxt, rew = self._expand(robot, humans, hb)
-        V = self._value(nxt, nh, A).view(N, A)
-        vals = rew + self.get_normalized_gamma() * V
+        V = self._value(nxt, nh, A)
+        groups = None
         if self.sparse_search:
-            # walk by descending value (ties: higher index first), keep the first action of each unseen group
-            order = (A - 1) - torch.argsort(-vals.flip(1), dim=1, stable=True)
-            g = self._groups_dev[order]                                       # group of each visited action
-            G = self._num_groups
-            assert width <= G, 'sparse search keeps at most one action per group'
-            onehot = torch.nn.functional.one_hot(g, G)
-            first = (onehot.cumsum(1) * onehot).sum(2) == 1                   # first visit of its group
-            rank = first.cumsum(1)
-            key = torch.where(first & (rank <= width), rank - 1, torch.full_like(rank, A + 1))
-            pos = torch.sort(key, dim=1, stable=True)[1][:, :width]
-            acts = torch.gather(order, 1, pos)
-        else:
-            acts = torch.argsort(-vals, dim=1, stable=True)[:, :width]       # top-width, ties by lower index
-        return acts, nxt, rew, nh
+            assert width <= self._num_groups, 'sparse search keeps at most one action per group'
+            groups = self._groups_dev
+        acts, crew, crob, value = ops.plan_select(rew, V, N, A, self.get_normalized_gamma(), width, groups=groups,
+                                                   next_robot=nxt, want_value=want_value)
+        return dict(acts=acts, rew=crew, robot=crob, nh=nh, all_rew=rew, nxt=nxt, value=value)
 
     def _V_planning(self, robot, humans, hb, depth, width):
         """V_planning (:271-302) for N states.  Returns (ret[N], node) where node holds what get_traj needs."""
@@ -256,48 +251,39 @@ class ModelPredictiveRL(Policy):
         if depth == 1:
             return v, None
         if self.do_action_clip:
-            acts, nxt, rew, nh = self._clip(robot, humans, hb, width)
+            c = self._clip(robot, humans, hb, width)
+            acts, child_rew, child_robot, nh, w = c['acts'], c['rew'], c['robot'], c['nh'], width
         else:
-            acts = torch.arange(A, device=robot.device).unsqueeze(0).expand(N, A)
             nh = self._next_humans(robot, humans, hb)
-            nxt, rew = self._expand(robot, humans, hb)
-        w = acts.size(1)
-        flat = (torch.arange(N, device=robot.device).unsqueeze(1) * A + acts).reshape(-1)
-        child_robot = nxt[flat]                                    # [N*w,1,9]
-        child_rew = torch.gather(rew, 1, acts)                     # [N,w]
+            child_robot, child_rew = self._expand(robot, humans, hb)
+            acts, w = None, A
         nv, child = self._V_planning(child_robot, nh, w, depth - 1, self.planning_width)
-        ret = v.unsqueeze(1) / depth + (depth - 1) / depth * (self.get_normalized_gamma() * nv.view(N, w) + child_rew)
-        best = torch.argmax(ret, dim=1)                            # first maximum wins (np.argmax, :298)
+        ret, best = ops.plan_backup(v, nv, child_rew, N, w, self.get_normalized_gamma(), depth)     # first maximum wins (np.argmax, :298)
         node = dict(acts=acts, best=best, rew=child_rew, child_robot=child_robot, child_humans=nh, child=child, w=w)
-        return torch.gather(ret, 1, best.unsqueeze(1)).squeeze(1), node
+        return ret, node
 
     def predict_batch(self, robot, humans, return_details=False):
         """Greedy branch of predict() (:212-233) for E root states at once.
 
         robot[E,1,9], humans[E,Nh,5] on self.device -> best action index [E] (int32, -1 if no finite value).
+        Every step is a hand-written kernel: no ATen op runs between the input tensors and the chosen actions.
         """
         if self.action_space is None:
             self.build_action_space(self.v_pref)
+        self._action_table()
         E, A = robot.size(0), len(self.action_space)
         with torch.no_grad():
             if self.do_action_clip:
-                acts, nxt, rew, nh = self._clip(robot, humans, 1, self.planning_width)
+                c = self._clip(robot, humans, 1, self.planning_width)
+                acts, nh, rew, nxt, w = c['acts'], c['nh'], c['all_rew'], c['nxt'], self.planning_width
+                ret, node = self._V_planning(c['robot'], nh, w, self.planning_depth, self.planning_width)
+                value, best, best_action = ops.plan_argmax(c['rew'].reshape(-1), ret, E, w, self.get_normalized_gamma(), act_map=acts)
             else:
                 acts = None
                 nh = self._next_humans(robot, humans, 1)
                 nxt, rew = self._expand(robot, humans, 1)
-            if acts is None:
                 ret, node = self._V_planning(nxt, nh, A, self.planning_depth, self.planning_width)
-                value, best = ops.plan_argmax(rew.reshape(-1), ret, E, A, self.get_normalized_gamma())
-                best_action = best
-            else:
-                w = acts.size(1)
-                flat = (torch.arange(E, device=robot.device).unsqueeze(1) * A + acts).reshape(-1)
-                ret, node = self._V_planning(nxt[flat], nh, w, self.planning_depth, self.planning_width)
-                crew = torch.gather(rew, 1, acts).contiguous()
-                value, best = ops.plan_argmax(crew.reshape(-1), ret, E, w, self.get_normalized_gamma())
-                best_action = torch.where(best >= 0, torch.gather(acts, 1, best.clamp(min=0).long().unsqueeze(1)).squeeze(1).int(),
-                                          best)
+                value, best, best_action = ops.plan_argmax(rew.reshape(-1), ret, E, A, self.get_normalized_gamma())
         if return_details:
             return best_action, dict(value=value, best=best, acts=acts, rew=rew, next_robot=nxt, next_humans=nh, node=node, ret=ret)
         return best_action
@@ -318,8 +304,12 @@ class ModelPredictiveRL(Policy):
         if self.action_space is None:
             self.build_action_space(self.v_pref)
         self._action_table()
+        # everything the capture bakes in as a host scalar, a flag or a pointer is part of the key
+        sp_g = getattr(self.state_predictor, 'graph_model', None)
         key = (robot.size(0), humans.size(1), self.planning_depth, self.planning_width, bool(self.do_action_clip),
-               bool(self.sparse_search), float(self.time_step), str(robot.device))
+               bool(self.sparse_search), float(self.time_step), str(robot.device), float(self.get_normalized_gamma()),
+               self.kinematics, bool(self.linear_state_predictor), id(self.value_estimator), id(self.state_predictor),
+               self.value_estimator.graph_model.flags(), sp_g.flags() if sp_g is not None else 0, len(self.action_space))
         self._refresh_packed_weights()
         entry = self._graphs.get(key)
         if entry is None:
@@ -375,18 +365,18 @@ class ModelPredictiveRL(Policy):
 
     def _build_traj(self, robot, humans, det, b):
         """[(state, action, reward), ...] along the best branch, as the reference's max_traj (:231, :295-300)."""
-        A = len(self.action_space)
         k = int(det['best'][0])                       # position inside the evaluated action list
-        traj = [((robot, humans), self.action_space[b], float(det['rew'][0, b]))]
+        traj = [((robot.clone(), humans.clone()), self.action_space[b], float(det['rew'][0, b]))]
         idx = b if det['acts'] is None else k         # row of the child in the level-1 batch
-        state = (det['next_robot'][b:b + 1], det['next_humans'][0:1])
+        # (the tensors are cloned: with CUDA-graph replay `det` aliases graph-private buffers the next predict() overwrites)
+        state = (det['next_robot'][b:b + 1].clone(), det['next_humans'][0:1].clone())
         node = det['node']
         while node is not None:
             kb = int(node['best'][idx])
-            a = int(node['acts'][idx, kb])
+            a = kb if node['acts'] is None else int(node['acts'][idx, kb])
             traj.append((state, self.action_space[a], float(node['rew'][idx, kb])))
             w = node['w']
-            state = (node['child_robot'][idx * w + kb: idx * w + kb + 1], node['child_humans'][idx: idx + 1])
+            state = (node['child_robot'][idx * w + kb: idx * w + kb + 1].clone(), node['child_humans'][idx: idx + 1].clone())
             idx = idx * w + kb
             node = node['child']
         traj.append((state, None, None))
@@ -395,12 +385,18 @@ class ModelPredictiveRL(Policy):
     # ------------------------------------------------------------------ reference-shaped helpers
     def action_clip(self, state, action_space, width, depth=1):
         """Reference signature (:242): state = (robot[1,1,9], humans[1,Nh,5]) -> list of `width` actions."""
+        if self.action_space is None:
+            self.build_action_space(self.v_pref)
+        self._action_table()
         with torch.no_grad():
-            acts = self._clip(state[0], state[1], 1, width)[0]
+            acts = self._clip(state[0], state[1], 1, width)['acts']
         return [action_space[int(i)] for i in acts[0]]
 
     def V_planning(self, state, depth, width):
         """Reference signature (:271): returns (value[1,1], trajectory placeholder)."""
+        if self.action_space is None:
+            self.build_action_space(self.v_pref)
+        self._action_table()
         with torch.no_grad():
             ret, _ = self._V_planning(state[0], state[1], 1, depth, width)
         return ret.view(1, 1), [(state, None, None)]
@@ -411,8 +407,8 @@ class ModelPredictiveRL(Policy):
             robot, humans = state
         else:
             robot, humans = joint_state_to_tensors(state, self.device)
-        act = torch.tensor([[action.vx, action.vy]], dtype=torch.float64, device=robot.device)
-        _, rew = ops.plan_expand(robot, humans, act, self.time_step, want_next=False)
+        act = torch.tensor([[action[0], action[1]]], dtype=torch.float64, device=robot.device)      # ActionXY (vx, vy) | ActionRot (v, r)
+        _, rew = ops.plan_expand(robot, humans, act, self.time_step, want_next=False, kinematics=self.kinematics)
         return float(rew[0])
 
     def transform(self, state):

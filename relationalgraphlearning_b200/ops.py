@@ -181,31 +181,71 @@ def gcn_layer(X, W, A=None, w_a=None, skip=False, return_A=False):
     return (Hout, Aout) if return_A else Hout
 
 
-def plan_expand(robot, humans, actions, time_step, humans_bcast=1, want_next=True, want_reward=True):
-    """robot[E,1,9], humans[E/humans_bcast,Nh,5], actions double[A,2] -> next_robot[E*A,1,9], reward[E*A]."""
+def plan_expand(robot, humans, actions, time_step, humans_bcast=1, want_next=True, want_reward=True, kinematics='holonomic'):
+    """robot[E,1,9], humans[E/humans_bcast,Nh,5], actions double[A,2] ((vx,vy) holonomic | (v,r) unicycle)
+    -> next_robot[E*A,1,9], reward[E*A]."""
     robot, humans = _check_state(robot, humans)
     E, Nh, A = robot.size(0), humans.size(1), actions.size(0)
     assert actions.dtype == torch.float64 and actions.is_cuda and actions.is_contiguous()
+    assert humans.size(0) * humans_bcast >= E, 'humans must cover every state (humans.size(0) * humans_bcast >= E)'
     nxt = torch.empty(E * A, 1, 9, dtype=torch.float32, device=robot.device) if want_next else None
     rew = torch.empty(E * A, dtype=torch.float32, device=robot.device) if want_reward else None
+    kin = _lib.KIN_HOLONOMIC if kinematics == 'holonomic' else _lib.KIN_UNICYCLE
     with torch.cuda.device(robot.device):
         rc = _lib.lib().rgl_plan_expand(_lib.ptr(robot), _lib.ptr(humans), E, Nh, humans_bcast, _lib.ptr(actions), A, float(time_step),
-                                        _lib.ptr(nxt), _lib.ptr(rew), _lib.stream_ptr(robot.device))
+                                        kin, _lib.ptr(nxt), _lib.ptr(rew), _lib.stream_ptr(robot.device))
     _lib.check(rc, 'rgl_plan_expand')
     _count(1 if E > 0 else 0)
     return nxt, rew
 
 
-def plan_argmax(reward, V, E, A, gamma_bar, want_value=True):
+def plan_argmax(reward, V, E, A, gamma_bar, want_value=True, act_map=None):
+    """value[E,A] = reward + gamma_bar * V; best[E] = first maximum (-1: none); with act_map[E,A] (int32) also
+    best_action[E] = act_map[e, best[e]].  Returns (value, best, best_action)."""
     reward, V = _f32c(reward), _f32c(V)
     value = torch.empty(E, A, dtype=torch.float32, device=V.device) if want_value else None
     best = torch.empty(E, dtype=torch.int32, device=V.device)
+    best_action = torch.empty(E, dtype=torch.int32, device=V.device) if act_map is not None else None
+    if act_map is not None:
+        assert act_map.dtype == torch.int32 and act_map.is_contiguous() and act_map.numel() == E * A
     with torch.cuda.device(V.device):
         rc = _lib.lib().rgl_plan_argmax(_lib.ptr(reward), _lib.ptr(V), E, A, float(gamma_bar), _lib.ptr(value),
-                                        _lib.ptr(best), _lib.stream_ptr(V.device))
+                                        _lib.ptr(best), _lib.ptr(act_map), _lib.ptr(best_action), _lib.stream_ptr(V.device))
     _lib.check(rc, 'rgl_plan_argmax')
     _count(1 if E > 0 else 0)
-    return value, best
+    return value, best, (best_action if act_map is not None else best)
+
+
+def plan_select(reward, V, E, A, gamma_bar, width, groups=None, next_robot=None, want_value=False):
+    """action_clip for E states: -> (acts[E,width] int32, child_reward[E,width], child_robot[E*width,1,9] | None, value[E,A] | None)."""
+    reward, V = _f32c(reward), _f32c(V)
+    dev = V.device
+    acts = torch.empty(E, width, dtype=torch.int32, device=dev)
+    crew = torch.empty(E, width, dtype=torch.float32, device=dev)
+    crob = torch.empty(E * width, 1, 9, dtype=torch.float32, device=dev) if next_robot is not None else None
+    value = torch.empty(E, A, dtype=torch.float32, device=dev) if want_value else None
+    if groups is not None:
+        assert groups.dtype == torch.int32 and groups.is_contiguous() and groups.numel() == A
+    with torch.cuda.device(dev):
+        rc = _lib.lib().rgl_plan_select(_lib.ptr(reward), _lib.ptr(V), E, A, float(gamma_bar), int(width), _lib.ptr(groups),
+                                        _lib.ptr(_f32c(next_robot)) if next_robot is not None else None, _lib.ptr(acts), _lib.ptr(crew),
+                                        _lib.ptr(crob), _lib.ptr(value), _lib.stream_ptr(dev))
+    _lib.check(rc, 'rgl_plan_select')
+    _count(1 if E > 0 else 0)
+    return acts, crew, crob, value
+
+
+def plan_backup(v, next_v, reward, E, W, gamma_bar, depth):
+    """V_planning backup: (ret_best[E], best[E] int32) over ret[e,k] = v/depth + (depth-1)/depth * (gamma_bar*next_v + reward)."""
+    v, next_v, reward = _f32c(v), _f32c(next_v), _f32c(reward)
+    ret = torch.empty(E, dtype=torch.float32, device=v.device)
+    best = torch.empty(E, dtype=torch.int32, device=v.device)
+    with torch.cuda.device(v.device):
+        rc = _lib.lib().rgl_plan_backup(_lib.ptr(v), _lib.ptr(next_v), _lib.ptr(reward), E, W, float(gamma_bar), int(depth),
+                                        _lib.ptr(ret), _lib.ptr(best), _lib.stream_ptr(v.device))
+    _lib.check(rc, 'rgl_plan_backup')
+    _count(1 if E > 0 else 0)
+    return ret, best
 
 
 # ---------------------------------------------------------------- autograd glue -------------------

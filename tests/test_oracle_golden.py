@@ -164,3 +164,21 @@ def test_vendored_reference_modules_reproduce_the_goldens():
             assert torch.equal(g1((g['robot'], g['humans'])), g['H'])
             assert torch.equal(ve((g['robot'], g['humans'])), g['V'])
             assert torch.equal(sp((g['robot'], g['humans']), None)[1], g['S'])
+
+
+def test_planner_unicycle_matches_reference():
+    """ActionRot / unicycle branch (model_predictive_rl.py:204,319-321,337-340; state_predictor.py:53-58, including its
+    element-7 indexing): the reference's own depth-1 predict() vs the restated tree, bit for bit."""
+    g = load_golden('planner_d1_unicycle_nh5')
+    torch.set_num_threads(1)
+    pl = P.OraclePlanner(g['graph1'], g['value'], g['graph2'], g['motion'], kinematics='unicycle')
+    assert np.array_equal(pl.actions, np.asarray(g['actions']))
+    for b in range(g['robot'].shape[0]):
+        robot, humans = g['robot'][b:b + 1], g['humans'][b:b + 1]
+        a, v, table = pl.predict(robot, humans)
+        assert a == int(g['chosen'][b])
+        if not table:
+            continue
+        assert np.array_equal(np.array([table[i] for i in range(81)]), np.asarray(g['values'][b], dtype=np.float64))
+        rew = np.array([pl.R((robot, humans), i) for i in range(81)], dtype=np.float64)
+        assert np.array_equal(rew, np.asarray(g['rewards'][b], dtype=np.float64))

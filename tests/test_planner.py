@@ -169,6 +169,29 @@ def test_tree_planning_matches_oracle(cfg, cuda_device):
             assert abs(max(got.values()) - v) <= 1e-4, (cfg, b, got, table)
 
 
+@pytest.mark.gpu
+def test_unicycle_predict_matches_reference_golden(cuda_device):
+    """ActionRot kinematics: per-action values, rewards and chosen actions of the reference's depth-1 predict()."""
+    from relationalgraphlearning_b200.simtypes import ActionRot
+    g = load_golden('planner_d1_unicycle_nh5')
+    pol = make_policy(g, cuda_device, kinematics='unicycle')
+    pol.build_action_space(1.0)
+    assert np.array_equal(np.array([[a.v, a.r] for a in pol.action_space]), np.asarray(g['actions']))
+    robot, humans = g['robot'].to(cuda_device), g['humans'].to(cuda_device)
+    best, det = pol.predict_batch(robot, humans, return_details=True)
+    ref = np.asarray(g['values'], dtype=np.float64)
+    assert np.abs(det['value'].cpu().double().numpy() - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())
+    assert np.abs(det['rew'].cpu().double().numpy() - np.asarray(g['rewards'], dtype=np.float64)).max() <= 1e-6
+    for b in range(robot.size(0)):
+        order = np.sort(ref[b])[::-1]
+        a = pol.predict(joint_state(g['robot'], g['humans'], b))
+        assert isinstance(a, ActionRot)
+        if int(g['chosen'][b]) != 0 or order[0] - order[1] > 1e-5:
+            assert a == pol.action_space[int(g['chosen'][b])], b
+    r = pol.estimate_reward(joint_state(g['robot'], g['humans'], 1), pol.action_space[7])
+    assert abs(r - float(g['rewards'][1][7])) <= 1e-7
+
+
 TREE_CASES = ['planner_d2w2_nh5', 'planner_d2w2_a81_nh5', 'planner_d3w2_nh5', 'planner_d2w3_sparse_nh5']
 
 
