@@ -216,6 +216,20 @@ int rgl_attn_layer_bwd(const float* A, const float* Hprev, const float* gM, cons
 int rgl_sim_bwd(const float* A, const float* gA, const float* X, const float* Y, float* gY, float* gX,
                 int B, int n, rgl_stream_t stream);
 
+/* ---- GPU-resident replay memory --------------------------------------------------------------------------------
+ * crowd_nav/utils/memory.py:4-28 keeps python tuples of tiny tensors and torch's DataLoader collates 6 x batch_size of
+ * them per minibatch (crowd_nav/utils/trainer.py:66-67,113-114).  Here a transition is one contiguous record of
+ * rgl_replay_record_floats(Nh) = 20 + 10*Nh floats in a caller-owned device array `store` [capacity, rec]:
+ *   [ robot 9 | humans 5*Nh | value 1 | reward 1 | next_robot 9 | next_humans 5*Nh ]
+ * rgl_replay_push writes one transition (six DEVICE tensors) into `slot`; rgl_replay_gather builds a minibatch in one
+ * launch: for b < B, record idx[b] (DEVICE int64) is scattered into robot[B,1,9], humans[B,Nh,5], value[B,1],
+ * reward[B,1], next_robot[B,1,9], next_humans[B,Nh,5]. */
+int rgl_replay_record_floats(int Nh);
+int rgl_replay_push(float* store, long long slot, int Nh, const float* robot, const float* humans, const float* value,
+                    const float* reward, const float* next_robot, const float* next_humans, rgl_stream_t stream);
+int rgl_replay_gather(const float* store, const long long* idx, int B, int Nh, float* robot, float* humans, float* value,
+                      float* reward, float* next_robot, float* next_humans, rgl_stream_t stream);
+
 /* ---- data-parallel gradient exchange (one process per GPU, NVLink peer memory) ----------------------------------
  * Data-parallel form of crowd_nav/utils/trainer.py:122-131,143-149: every rank back-propagates its shard of the
  * minibatch, then ONE sum over a flat fp32 buffer holding every gradient (22 813 floats = 91 252 B for the value

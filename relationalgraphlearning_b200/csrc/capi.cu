@@ -266,4 +266,25 @@ int rgl_sim_bwd(const float* A, const float* gA, const float* X, const float* Y,
     return e == cudaSuccess ? RGL_OK : fail_cuda(e, "rgl_sim_bwd");
 }
 
+int rgl_replay_record_floats(int Nh) { return Nh < 1 || Nh > RGL_MAX_HUMANS ? 0 : 2 * RGL_ROBOT_DIM + 2 * RGL_HUMAN_DIM * Nh + 2; }
+
+int rgl_replay_push(float* store, long long slot, int Nh, const float* robot, const float* humans, const float* value,
+                    const float* reward, const float* next_robot, const float* next_humans, rgl_stream_t stream) {
+    if (!store || slot < 0 || !robot || !humans || !value || !reward || !next_robot || !next_humans)
+        return fail(RGL_EINVAL, "rgl_replay_push: bad argument");
+    if (Nh < 1 || Nh > RGL_MAX_HUMANS) return fail(RGL_EUNSUPPORTED, "rgl_replay_push: human count outside [1,31]");
+    cudaError_t e = rgl::run_replay_push(store, slot, Nh, robot, humans, value, reward, next_robot, next_humans, (cudaStream_t)stream);
+    return e == cudaSuccess ? RGL_OK : fail_cuda(e, "rgl_replay_push");
+}
+
+int rgl_replay_gather(const float* store, const long long* idx, int B, int Nh, float* robot, float* humans, float* value,
+                      float* reward, float* next_robot, float* next_humans, rgl_stream_t stream) {
+    if (B == 0) return RGL_OK;
+    if (!store || !idx || B < 0 || !robot || !humans || !value || !reward || !next_robot || !next_humans)
+        return fail(RGL_EINVAL, "rgl_replay_gather: bad argument");
+    if (Nh < 1 || Nh > RGL_MAX_HUMANS) return fail(RGL_EUNSUPPORTED, "rgl_replay_gather: human count outside [1,31]");
+    cudaError_t e = rgl::run_replay_gather(store, idx, B, Nh, robot, humans, value, reward, next_robot, next_humans, (cudaStream_t)stream);
+    return e == cudaSuccess ? RGL_OK : fail_cuda(e, "rgl_replay_gather");
+}
+
 }  // extern "C"
