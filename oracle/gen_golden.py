@@ -40,13 +40,14 @@ def sd_np(sd, prefix):
     return {prefix + k: v.detach().cpu().numpy() for k, v in sd.items()}
 
 
-def build_modules(seed, layerwise=False, skip=True, scale=None):
+def build_modules(seed, layerwise=False, skip=True, scale=None, similarity='embedded_gaussian'):
     from crowd_nav.policy.graph_model import RGL
     from crowd_nav.policy.value_estimator import ValueEstimator
     from crowd_nav.policy.state_predictor import StatePredictor
     cfg = load_ref_config('mp_separate').PolicyConfig()
     cfg.gcn.layerwise_graph = layerwise
     cfg.gcn.skip_connection = skip
+    cfg.gcn.similarity_function = similarity
     torch.manual_seed(seed)
     g1 = RGL(cfg, 9, 5)
     ve = ValueEstimator(cfg, g1)
@@ -55,14 +56,15 @@ def build_modules(seed, layerwise=False, skip=True, scale=None):
     if scale is not None:
         with torch.no_grad():
             for g in (g1, g2):
-                g.w_a.mul_(scale)
+                if isinstance(getattr(g, 'w_a', None), torch.nn.Parameter):
+                    g.w_a.mul_(scale)
                 for w in g.Ws:
                     w.mul_(scale)
     return cfg, g1, ve, g2, sp
 
 
-def forward_case(name, seed, nh, batch, layerwise=False, skip=True, scale=None, data_seed=1234):
-    cfg, g1, ve, g2, sp = build_modules(seed, layerwise, skip, scale)
+def forward_case(name, seed, nh, batch, layerwise=False, skip=True, scale=None, data_seed=1234, similarity='embedded_gaussian'):
+    cfg, g1, ve, g2, sp = build_modules(seed, layerwise, skip, scale, similarity)
     robot, humans = synthetic_states(batch, nh, seed=data_seed)
     out = {}
     with torch.no_grad():
@@ -71,9 +73,14 @@ def forward_case(name, seed, nh, batch, layerwise=False, skip=True, scale=None, 
         V = ve((robot, humans))
         S = sp((robot, humans), None)[1]
         g1.double(); ve.double(); g2.double(); sp.double()
-        H64 = g1((robot.double(), humans.double())).clone()
-        V64 = ve((robot.double(), humans.double()))
-        S64 = sp((robot.double(), humans.double()), None)[1]
+        try:
+            H64 = g1((robot.double(), humans.double())).clone()
+            V64 = ve((robot.double(), humans.double()))
+            S64 = sp((robot.double(), humans.double()), None)[1]
+        except RuntimeError:
+            # equal_attention / diagonal build a float32 A whatever the input dtype (graph_model.py:91-93): the reference
+            # itself cannot run them in fp64; the fp32 outputs stand in
+            H64, V64, S64 = H.double(), V.double(), S.double()
         g1.float(); ve.float(); g2.float(); sp.float()
     out.update(sd_np(g1.state_dict(), 'graph1/'))
     out.update(sd_np(ve.value_network.state_dict(), 'value/'))
@@ -83,6 +90,8 @@ def forward_case(name, seed, nh, batch, layerwise=False, skip=True, scale=None, 
                H64=H64.numpy(), V64=V64.numpy(), S64=S64.numpy(),
                meta=np.array([seed, nh, batch, int(layerwise), int(skip), data_seed], dtype=np.int64),
                scale=np.array([1.0 if scale is None else scale]))
+    if similarity != 'embedded_gaussian':
+        out['similarity'] = np.array(similarity)
     np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
     print('wrote', name, 'V range', float(V.min()), float(V.max()), '|H|max', float(H.abs().max()))
 
@@ -231,6 +240,9 @@ def planner_tree_case(name, seed, nh, n_states, depth, width, sparse=False, spee
     print('wrote', name, 'chosen', chosen, 'kept', kept, 'traj', trajs)
 
 
+SIMILARITIES = ['gaussian', 'cosine', 'cosine_softmax', 'concatenation', 'squared', 'equal_attention', 'diagonal']
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)
@@ -245,6 +257,9 @@ def main():
     forward_case('fwd_nh5_adversarial', 2, 5, 64, scale=4.0)   # softmax saturation
     forward_case('fwd_nh5_layerwise_noskip', 0, 5, 64, layerwise=True, skip=False)   # BasePolicyConfig defaults
     forward_case('fwd_nh5_layerwise_skip', 1, 5, 64, layerwise=True, skip=True)
+    # the seven other similarity functions of graph_model.py:67-93 (trained-like scale keeps the un-normalised ones finite)
+    for sim in SIMILARITIES:
+        forward_case('fwd_nh5_sim_' + sim, 3, 5, 16, layerwise=(sim in ('gaussian', 'squared')), scale=0.2, similarity=sim)
     planner_case('planner_d1_nh5', 0, 5, 8)
     planner_case('planner_d1_unicycle_nh5', 1, 5, 6, data_seed=78, kinematics='unicycle')     # ActionRot branch (:204,:319-321,:337-340)
     # depth > 1 look-ahead with action clipping, through the one-line-patched copy of the reference planner

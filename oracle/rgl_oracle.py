@@ -60,6 +60,12 @@ def similarity(X, sd, kind='embedded_gaussian'):
         A = A * A
         return A / torch.sum(A, dim=2, keepdim=True)
     n = X.size(1)
+    if kind == 'concatenation':
+        # A[i][j] = w_a([X_i | X_j]) with w_a = mlp(2*X_dim, [2*X_dim, 1], last_relu=True), no normalisation (:81-86)
+        import itertools
+        idx = torch.LongTensor([p for p in itertools.product(range(n), repeat=2)]).reshape(-1)
+        pair = torch.index_select(X, 1, idx).reshape(-1, n * n, X.size(2) * 2)
+        return mlp(pair, sd, 'w_a.', last_relu=True).reshape(-1, n, n)
     if kind == 'equal_attention':
         return (torch.ones(n, n, dtype=X.dtype) / n).expand(X.size(0), n, n)
     if kind == 'diagonal':

@@ -12,6 +12,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, 'librgl_b200.so')
 
 MAX_LAYERS = 4
+MAX_HUMANS = 31
 FLAG_SKIP = 1
 FLAG_LAYERWISE = 2
 FLAG_THROUGHPUT = 4

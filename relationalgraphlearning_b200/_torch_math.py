@@ -1,12 +1,14 @@
-"""Differentiable torch-op statement of the path, used ON THE GPU for two things only:
+"""Differentiable torch-op statement of the path, on whatever device its tensors live.  Used for
 
-  * the backward pass of the CUDA forward ops until the hand-written backward kernels land
-    (autograd recompute on the same device as the inputs), and
-  * graph configurations the sm_100a kernels are not specialised for (similarity functions other
-    than 'embedded_gaussian', non-default layer widths).
+  * graph configurations the sm_100a kernels are not specialised for: the seven similarity functions other than
+    'embedded_gaussian' (graph_model.py:67-93; no shipped config selects them), non-default layer widths, human
+    counts outside 1..31 -- on the GPU, checked against reference-minted goldens (tests/test_gpu_parity.py);
+  * the backward pass of layerwise-graph configurations (autograd recompute on the inputs' device);
+  * modules whose parameters live on the CPU and are called with CPU tensors (the reference's callers
+    may keep a policy on the CPU) -- ops.require_cuda_or_cpu_module states the policy.
 
-It is never a substitute for a missing librgl_b200.so: the forward ops raise if the library cannot
-be loaded, and CPU tensors are rejected by the modules.
+It is never a substitute for a missing librgl_b200.so: CUDA tensors always go through the kernels, and every op on
+that path raises if the library cannot be loaded.
 Math follows crowd_nav/policy/graph_model.py:63-130, value_estimator.py:18-19, state_predictor.py:28,36.
 """
 import torch

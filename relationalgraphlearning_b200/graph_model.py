@@ -107,11 +107,17 @@ class RGL(nn.Module):
             self._A_dev, self._A_host = out['A0'], None
         return out
 
+    def shape_supported(self, humans):
+        """The fused kernels hold one state's nodes in one 128-row tile: 1..31 humans (include/rgl_b200.h RGL_MAX_HUMANS)."""
+        return 1 <= humans.size(1) <= _lib.MAX_HUMANS
+
     def forward(self, state):
         robot, humans = state
-        if not (robot.is_cuda and humans.is_cuda):
-            raise _lib.RglError('RGL.forward: CUDA tensors required (this implementation has no CPU compute path)')
-        if not self.kernel_supported():
+        ops.require_cuda_or_cpu_module(self, robot, humans, 'RGL.forward')
+        # torch-op statement of the same math (_torch_math.py), on the tensors' own device: CPU modules (the reference's
+        # callers may keep a policy on the CPU, crowd_nav/train.py:82), the seven non-default similarity functions,
+        # non-default layer widths and human counts outside the kernels' 1..31
+        if not robot.is_cuda or not self.kernel_supported() or not self.shape_supported(humans):
             H, A = TM.graph_forward(self, robot, humans, return_A=True)
             if not self.layerwise_graph:
                 self._A_dev, self._A_host = A[0].detach(), None

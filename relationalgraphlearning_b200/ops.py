@@ -114,6 +114,23 @@ def packed_motion(seq, cache, force=False):
     return cache.get(params, int(lib.rgl_packed_motion_floats()), pack, force)
 
 
+def require_cuda_or_cpu_module(module, robot, humans, what):
+    """Device policy of the drop-in modules.  CUDA tensors ALWAYS run the sm_100a kernels (or raise: a missing library is
+    never papered over).  CPU tensors are accepted only by a module whose parameters live on the CPU -- a policy the
+    reference's caller never moved to a GPU -- and are then evaluated with the torch-op statement of the reference math
+    (_torch_math.py) on the CPU, as SURVEY.md 8(b) asks; RGL_FORBID_CPU=1 turns that into an error."""
+    if robot.is_cuda and humans.is_cuda:
+        _lib.lib()                      # raises if librgl_b200.so is missing
+        return
+    import os
+    p = next(module.parameters(), None)
+    if robot.is_cuda != humans.is_cuda or (p is not None and p.is_cuda):
+        raise _lib.RglError('%s: module and inputs must be on the same device (module on %s, robot on %s, humans on %s)' %
+                            (what, p.device if p is not None else '?', robot.device, humans.device))
+    if os.environ.get('RGL_FORBID_CPU'):
+        raise _lib.RglError('%s: CPU tensors refused (RGL_FORBID_CPU is set)' % what)
+
+
 # ---------------------------------------------------------------- raw forward ops ----------------
 def _check_state(robot, humans):
     if not (robot.is_cuda and humans.is_cuda):

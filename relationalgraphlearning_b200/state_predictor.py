@@ -85,10 +85,9 @@ class StatePredictor(nn.Module):
         assert len(state[0].shape) == 3
         assert len(state[1].shape) == 3
         robot, humans = state
-        if not (robot.is_cuda and humans.is_cuda):
-            raise _lib.RglError('StatePredictor.forward: CUDA tensors required (no CPU compute path)')
+        ops.require_cuda_or_cpu_module(self, robot, humans, 'StatePredictor.forward')
         next_robot = None if action is None else self.compute_next_state(robot, action)
-        if not self.kernel_supported():
+        if not robot.is_cuda or not self.kernel_supported() or not self.graph_model.shape_supported(humans):
             next_humans = self._torch_humans(robot, humans, detach)
         elif ops._needs_grad(self, robot, humans):
             from . import training

@@ -44,9 +44,8 @@ class ValueEstimator(nn.Module):
         assert len(state[0].shape) == 3
         assert len(state[1].shape) == 3
         robot, humans = state
-        if not (robot.is_cuda and humans.is_cuda):
-            raise _lib.RglError('ValueEstimator.forward: CUDA tensors required (no CPU compute path)')
-        if not self.kernel_supported():
+        ops.require_cuda_or_cpu_module(self, robot, humans, 'ValueEstimator.forward')
+        if not robot.is_cuda or not self.kernel_supported() or not self.graph_model.shape_supported(humans):
             return self.value_network(self.graph_model(state)[:, 0, :])
         if ops._needs_grad(self, robot, humans):
             from . import training

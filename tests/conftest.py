@@ -24,6 +24,8 @@ def load_golden(name):
         if '/' in k:
             grp, key = k.split('/', 1)
             out[grp][key] = torch.from_numpy(z[k])
+        elif z[k].dtype.kind == 'U':
+            out[k] = str(z[k])
         else:
             out[k] = torch.from_numpy(z[k]) if z[k].dtype.kind == 'f' else z[k]
     return out
@@ -33,8 +35,14 @@ FWD_CASES = ['fwd_nh5_s0', 'fwd_nh5_s1', 'fwd_nh5_s2', 'fwd_nh5_b1', 'fwd_nh10_s
              'fwd_nh5_trained', 'fwd_nh5_adversarial', 'fwd_nh5_layerwise_noskip', 'fwd_nh5_layerwise_skip']
 
 
+SIM_CASES = ['fwd_nh5_sim_' + s for s in ('gaussian', 'cosine', 'cosine_softmax', 'concatenation', 'squared', 'equal_attention', 'diagonal')]
+
+
 def graph_kw(g):
-    return dict(layerwise_graph=bool(g['meta'][3]), skip_connection=bool(g['meta'][4]))
+    kw = dict(layerwise_graph=bool(g['meta'][3]), skip_connection=bool(g['meta'][4]))
+    if 'similarity' in g:
+        kw['similarity_function'] = g['similarity']
+    return kw
 
 
 def assert_close_scaled(got, ref, rel=1e-5, name=''):

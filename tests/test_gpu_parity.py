@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import FWD_CASES, assert_close_scaled, graph_kw, load_golden
+from conftest import FWD_CASES, SIM_CASES, assert_close_scaled, graph_kw, load_golden
 from oracle import rgl_oracle as O
 from relationalgraphlearning_b200 import _lib, ops
 from relationalgraphlearning_b200.config import policy_config
@@ -21,7 +21,8 @@ REL = 1e-5
 
 def modules_from_golden(g, dev):
     kw = graph_kw(g)
-    cfg = policy_config(layerwise_graph=kw['layerwise_graph'], skip_connection=kw['skip_connection'])
+    cfg = policy_config(layerwise_graph=kw['layerwise_graph'], skip_connection=kw['skip_connection'],
+                        similarity_function=kw.get('similarity_function', 'embedded_gaussian'))
     g1 = RGL(cfg, 9, 5)
     ve = ValueEstimator(cfg, g1)
     g2 = RGL(cfg, 9, 5)
@@ -59,6 +60,77 @@ def test_forward_matches_reference_golden(case, cuda_device):
         e_ref = float((r32.double() - r64).abs().max())
         e_got = float((got.double().cpu() - r64).abs().max())
         assert e_got <= 4.0 * e_ref + 2e-6 * scale, (case, nm, e_got, e_ref)
+
+
+@pytest.mark.parametrize('case', SIM_CASES)
+def test_other_similarity_functions_match_reference_golden(case, cuda_device):
+    """The seven similarity functions the fused kernel is not specialised for (graph_model.py:67-93) run as torch ops on
+    the GPU; fixtures minted from the reference modules."""
+    g = load_golden(case)
+    g1, ve, g2, sp = modules_from_golden(g, cuda_device)
+    assert not g1.kernel_supported()
+    robot, humans = g['robot'].to(cuda_device), g['humans'].to(cuda_device)
+    with torch.no_grad():
+        H, V, S = g1((robot, humans)), ve((robot, humans)), sp((robot, humans), None)[1]
+    assert_close_scaled(H, g['H'], REL, case + ':H')
+    assert_close_scaled(V, g['V'], REL, case + ':V')
+    assert_close_scaled(S, g['S'], REL, case + ':S')
+    # ... and train (autograd through the same torch ops)
+    ve((robot, humans)).sum().backward()
+    assert all(p.grad is not None for p in ve.value_network.parameters())
+
+
+@pytest.mark.parametrize('nh', [0, 32, 40])
+def test_human_counts_outside_the_kernel_range(nh, cuda_device):
+    """Nh = 0 or > 31: the modules still compute (torch ops on the GPU), like the reference does for any Nh."""
+    g = load_golden('fwd_nh5_s0')
+    g1, ve, g2, sp = modules_from_golden(g, cuda_device)
+    robot, humans = synthetic_states(9, max(nh, 1), seed=5)
+    humans = humans[:, :nh]
+    with torch.no_grad():
+        H, V, S = g1((robot.to(cuda_device), humans.to(cuda_device))), ve((robot.to(cuda_device), humans.to(cuda_device))), \
+            sp((robot.to(cuda_device), humans.to(cuda_device)), None)[1]
+        assert_close_scaled(H, O.rgl_forward(g['graph1'], robot, humans), REL, 'H')
+        assert_close_scaled(V, O.value_forward(g['graph1'], g['value'], robot, humans), REL, 'V')
+        assert S.shape == (9, nh, 5)
+        if nh:
+            assert_close_scaled(S, O.statepred_forward(g['graph2'], g['motion'], robot, humans), REL, 'S')
+
+
+def test_c2_every_state_against_the_oracle_with_error_histogram(cuda_device, capsys):
+    """BASELINE C2 (B = 4096, Nh = 5): ALL 4096 states against the CPU oracle, under the scaled bound of the comparator AND
+    reported element-wise: the distribution of |x - ref| / max(|ref|, 1e-3 * scale) (what '1e-5 rel' means element by
+    element; elements near zero are measured against 1e-3 of the tensor scale)."""
+    g = load_golden('fwd_nh5_s0')
+    g1, ve, g2, sp = modules_from_golden(g, cuda_device)
+    robot, humans = synthetic_states(4096, 5, seed=1234)
+    with torch.no_grad():
+        H, V, S = g1((robot.to(cuda_device), humans.to(cuda_device))), ve((robot.to(cuda_device), humans.to(cuda_device))), \
+            sp((robot.to(cuda_device), humans.to(cuda_device)), None)[1]
+        torch.set_num_threads(8)
+        Ho = O.rgl_forward(g['graph1'], robot, humans)
+        Vo = O.value_forward(g['graph1'], g['value'], robot, humans)
+        So = O.statepred_forward(g['graph2'], g['motion'], robot, humans)
+    lines = []
+    for nm, got, ref in (('H', H, Ho), ('V', V, Vo), ('S', S, So)):
+        assert_close_scaled(got, ref, REL, 'C2 all states ' + nm)
+        got, ref = got.double().cpu(), ref.double()
+        scale = float(ref.abs().max())
+        rel = (got - ref).abs() / torch.clamp(ref.abs(), min=1e-3 * scale)
+        qs = torch.quantile(rel.flatten()[:: max(1, rel.numel() // 1000000)], torch.tensor([0.5, 0.9, 0.99, 0.999], dtype=torch.float64))
+        frac = float((rel <= 1e-5).double().mean())
+        lines.append('%s: scale %.3g  max|err|/scale %.2e  elementwise rel p50 %.1e p90 %.1e p99 %.1e p99.9 %.1e max %.1e  frac<=1e-5 %.5f' %
+                     (nm, scale, float((got - ref).abs().max()) / scale, *[float(q) for q in qs], float(rel.max()), frac))
+        assert float(qs[0]) <= 1e-5, lines[-1]              # the typical element is within 1e-5 element-wise; the tail is reported
+    with capsys.disabled():
+        print('\n[C2 error histogram, 4096 states vs oracle]\n' + '\n'.join(lines))
+    import os
+    try:
+        os.makedirs(os.path.join(os.path.dirname(__file__), '..', 'gpurun_out'), exist_ok=True)
+        with open(os.path.join(os.path.dirname(__file__), '..', 'gpurun_out', 'c2_error_histogram.txt'), 'w') as f:
+            f.write('\n'.join(lines) + '\n')
+    except OSError:
+        pass
 
 
 @pytest.mark.parametrize('B', [0, 1, 2, 31, 33, 100, 257])

@@ -88,15 +88,34 @@ def test_deepcopy_gives_independent_target_model():
     assert not torch.equal(tgt.graph_model.w_a, ve.graph_model.w_a)
 
 
-def test_cpu_tensors_are_rejected_loudly():
-    _, g1, ve, _, sp = build(0)
-    robot, humans = torch.zeros(2, 1, 9), torch.zeros(2, 5, 5)
+def test_cpu_modules_accept_cpu_tensors_with_the_reference_math(monkeypatch):
+    """modules whose parameters live on the CPU accept CPU tensors (torch-op statement of the reference
+    math) -- outputs equal the reference-minted golden within fp32 round-off; RGL_FORBID_CPU=1 refuses instead."""
+    from conftest import assert_close_scaled, load_golden
+    g = load_golden('fwd_nh5_s0')
+    _, g1, ve, g2, sp = build(0)
+    g1.load_state_dict(g['graph1'])
+    ve.value_network.load_state_dict(g['value'])
+    g2.load_state_dict(g['graph2'])
+    sp.human_motion_predictor.load_state_dict(g['motion'])
+    with torch.no_grad():
+        assert_close_scaled(g1((g['robot'], g['humans'])), g['H'], 1e-6, 'H')
+        assert_close_scaled(ve((g['robot'], g['humans'])), g['V'], 1e-6, 'V')
+        nr, S = sp((g['robot'], g['humans']), None)
+        assert nr is None
+        assert_close_scaled(S, g['S'], 1e-6, 'S')
+    assert g1.A is not None and g1.A.shape == (6, 6)
+    # gradients flow on the CPU path too (the reference trainer on a CPU policy)
+    loss = ve((g['robot'], g['humans'])).sum()
+    loss.backward()
+    assert ve.graph_model.w_a.grad is not None and ve.value_network[0].weight.grad is not None
+    monkeypatch.setenv('RGL_FORBID_CPU', '1')
     with pytest.raises(_lib.RglError):
-        g1((robot, humans))
+        g1((g['robot'], g['humans']))
     with pytest.raises(_lib.RglError):
-        ve((robot, humans))
+        ve((g['robot'], g['humans']))
     with pytest.raises(_lib.RglError):
-        sp((robot, humans), None)
+        sp((g['robot'], g['humans']), None)
 
 
 def test_batched_next_robot_state_rule():

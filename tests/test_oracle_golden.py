@@ -182,3 +182,19 @@ def test_planner_unicycle_matches_reference():
         assert np.array_equal(np.array([table[i] for i in range(81)]), np.asarray(g['values'][b], dtype=np.float64))
         rew = np.array([pl.R((robot, humans), i) for i in range(81)], dtype=np.float64)
         assert np.array_equal(rew, np.asarray(g['rewards'][b], dtype=np.float64))
+
+
+from conftest import SIM_CASES  # noqa: E402
+
+
+@pytest.mark.parametrize('case', SIM_CASES)
+def test_similarity_variants_bit_exact_vs_reference(case):
+    """The seven other similarity functions (graph_model.py:67-93), fixtures minted from the reference modules."""
+    g = load_golden(case)
+    torch.set_num_threads(1)
+    kw = graph_kw(g)
+    with torch.no_grad():
+        H = O.rgl_forward(g['graph1'], g['robot'], g['humans'], **kw)
+        V = O.value_forward(g['graph1'], g['value'], g['robot'], g['humans'], **kw)
+        S = O.statepred_forward(g['graph2'], g['motion'], g['robot'], g['humans'], **kw)
+    assert torch.equal(H, g['H']) and torch.equal(V, g['V']) and torch.equal(S, g['S'])
