@@ -92,6 +92,13 @@ static_assert(TM_B1 + 8 <= TMOTION_FLOATS && tc_graph_floats(1) % 256 == 0, "ten
 static_assert(graph_floats(2) - (2 * HID + 3 * XD) * (LDW - XD) == 8256, "graph parameter count (SURVEY.md 2b) + row padding");
 static_assert(graph_floats(RGL_MAX_LAYERS) % 4 == 0 && VALUE_FLOATS % 4 == 0 && MOTION_FLOATS % 4 == 0, "16B sections");
 
+// ---- programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// while its predecessor on the stream is still running; it must execute pdl_wait() before it reads anything the predecessor
+// wrote (or writes anything the predecessor reads).  pdl_trigger() in the predecessor lets the dependent's launch latency and
+// prologue overlap the predecessor's tail.  Both are no-ops for kernels launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- PTX: mbarrier + TMA bulk copy (cp.async.bulk -> SASS UBLKCP) ------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

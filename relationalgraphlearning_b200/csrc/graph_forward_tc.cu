@@ -120,7 +120,6 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tc_kern
         }
     };
     int tile = blockIdx.x * G + grp;
-    load_raw(tile);                          // the first tile's raw rows: in flight under the prologue (TMEM allocation, weight TMA)
 
     if (warp == 0) tmem_alloc(tslot, TC_COLS * G);
     if (tid == 0) {
@@ -130,6 +129,10 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tc_kern
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    // PDL: everything above (TMEM allocation, barrier set-up) may overlap the tail of the previous kernel on the stream;
+    // the states, the packed weights and every output buffer are only touched after this point
+    pdl_wait();
+    load_raw(tile);                          // the first tile's raw rows: in flight under the weight TMA
     if (tid == 0) {
         // stage 0: layer-1 embedding tiles (the first MMA needs only these); stage 1: everything else
         const float* src = a.gw + graph_tc_off(a.L);
@@ -374,6 +377,9 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tc_kern
         }
 
         // ================= outputs =================
+        // PDL: this CTA's last tile has left the tensor pipe -- let the next kernel on the stream launch and run its
+        // prologue under the output phase (it waits for this grid to complete before it reads or writes memory)
+        if (tile + tstride >= ntiles) pdl_trigger();
         if (a.E != nullptr && is_robot && valid) {
             float* e = a.E + (s0 + s_loc) * XD;
 #pragma unroll
@@ -501,8 +507,7 @@ static cudaError_t launch_tc(const GraphArgs& a, int num_sms, size_t max_smem, c
     int tma_out = 0;
     if (a.H != nullptr && !(tma_env && tma_env[0] == '0'))
         tma_out = make_state_map(&mr, a.H, a.B, n, 1, spt) && make_state_map(&mh, a.H, a.B, n, n - 1, spt) ? 1 : 0;
-    graph_forward_tc_kernel<N, G><<<grid, 128 * G, smem, st>>>(b, mr, mh, tma_out);
-    return cudaGetLastError();
+    return launch_pdl(graph_forward_tc_kernel<N, G>, dim3(grid), dim3(128 * G), smem, st, b, mr, mh, tma_out);
 }
 
 template <int N>

@@ -1,6 +1,8 @@
 // Internal launch interface between capi.cu and the kernel translation units.
 #pragma once
 #include <mutex>
+#include <stdlib.h>
+#include <utility>
 #include "common.cuh"
 
 namespace rgl {
@@ -27,6 +29,21 @@ static inline cudaError_t ensure_dyn_smem_ptr(const void* kernel, int bytes) {
 }
 template <typename Kernel>
 static inline cudaError_t ensure_dyn_smem(Kernel kernel, int bytes) { return ensure_dyn_smem_ptr(reinterpret_cast<const void*>(kernel), bytes); }
+
+// Launch with the programmatic-stream-serialization attribute (PDL): only for kernels that call pdl_wait() before touching
+// memory a predecessor may have written.  RGL_PDL=0 launches them fully serialised (experiments / debugging).
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    static const char* env = getenv("RGL_PDL");
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (env && env[0] == '0') ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 typedef RglGraphSave GraphSave;      // optional activation saves of the training forward (include/rgl_b200.h)
 

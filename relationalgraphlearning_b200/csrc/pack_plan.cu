@@ -131,6 +131,8 @@ __global__ void plan_expand_kernel(const float* __restrict__ robot, const float*
                                    const double* __restrict__ actions, int A, double dt, int unicycle,
                                    float* __restrict__ next_robot, float* __restrict__ reward) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_wait();
+    pdl_trigger();
     if (idx >= E * A) return;
     const int e = idx / A, a = idx - e * A;
     const float* r = robot + (size_t)e * RD;
@@ -206,6 +208,8 @@ __global__ void plan_argmax_kernel(const float* __restrict__ reward, const float
                                    int* __restrict__ best_action) {
     const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
+    pdl_wait();
+    pdl_trigger();
     if (e >= E) return;
     float bv = -INFINITY;
     int bi = -1;
@@ -241,6 +245,8 @@ __global__ void plan_select_kernel(const float* __restrict__ reward, const float
                                    float* __restrict__ value) {
     const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
+    pdl_wait();
+    pdl_trigger();
     if (e >= E) return;
     float v[SEL_MAX_PER_LANE];
     unsigned taken = 0;                   // bit i: this lane's i-th action is no longer a candidate
@@ -310,6 +316,8 @@ __global__ void plan_backup_kernel(const float* __restrict__ v, const float* __r
                                    int W, float gamma_bar, float depth, float frac, float* __restrict__ ret_best,
                                    int* __restrict__ best) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_wait();
+    pdl_trigger();
     if (e >= E) return;
     const float base = __fdiv_rn(v[e], depth);
     float bv = 0.f;
@@ -338,25 +346,21 @@ cudaError_t run_pack_motion(const RglMotionParams& p, float* out, cudaStream_t s
 cudaError_t run_plan_expand(const float* robot, const float* humans, int E, int Nh, int hb, const double* actions, int A, double dt,
                             int unicycle, float* next_robot, float* reward, cudaStream_t st) {
     const int total = E * A;
-    plan_expand_kernel<<<(total + 127) / 128, 128, 0, st>>>(robot, humans, E, Nh, hb, actions, A, dt, unicycle, next_robot, reward);
-    return cudaGetLastError();
+    return launch_pdl(plan_expand_kernel, dim3((total + 127) / 128), dim3(128), 0, st, robot, humans, E, Nh, hb, actions, A, dt, unicycle, next_robot, reward);
 }
 cudaError_t run_plan_argmax(const float* reward, const float* V, int E, int A, float gamma_bar, float* value, int* best,
                             const int* act_map, int* best_action, cudaStream_t st) {
-    plan_argmax_kernel<<<(E + 3) / 4, 128, 0, st>>>(reward, V, E, A, gamma_bar, value, best, act_map, best_action);
-    return cudaGetLastError();
+    return launch_pdl(plan_argmax_kernel, dim3((E + 3) / 4), dim3(128), 0, st, reward, V, E, A, gamma_bar, value, best, act_map, best_action);
 }
 cudaError_t run_plan_select(const float* reward, const float* V, int E, int A, float gamma_bar, int width, const int* groups,
                             const float* next_robot, int* acts, float* child_rew, float* child_robot, float* value, cudaStream_t st) {
     if (A > 32 * SEL_MAX_PER_LANE) return cudaErrorInvalidConfiguration;
-    plan_select_kernel<<<(E + 3) / 4, 128, 0, st>>>(reward, V, E, A, gamma_bar, width, groups, next_robot, acts, child_rew, child_robot, value);
-    return cudaGetLastError();
+    return launch_pdl(plan_select_kernel, dim3((E + 3) / 4), dim3(128), 0, st, reward, V, E, A, gamma_bar, width, groups, next_robot, acts, child_rew, child_robot, value);
 }
 cudaError_t run_plan_backup(const float* v, const float* nv, const float* rew, int E, int W, float gamma_bar, int depth,
                             float* ret_best, int* best, cudaStream_t st) {
     const float frac = (float)((double)(depth - 1) / (double)depth);
-    plan_backup_kernel<<<(E + 127) / 128, 128, 0, st>>>(v, nv, rew, E, W, gamma_bar, (float)depth, frac, ret_best, best);
-    return cudaGetLastError();
+    return launch_pdl(plan_backup_kernel, dim3((E + 127) / 128), dim3(128), 0, st, v, nv, rew, E, W, gamma_bar, (float)depth, frac, ret_best, best);
 }
 
 }  // namespace rgl

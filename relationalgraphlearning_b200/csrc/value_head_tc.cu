@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(128 * G, 1) value_head_tc_kernel(const float* 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();      // PDL: the prologue above may overlap the tail of the kernel that produces E (common.cuh)
     if (tid == 0) {
         const float* src = vw + VALUE_TC_OFF;
         mbar_arrive_expect_tx(bars + 0, TV_W1 * 4u);                                  // layer 0 + biases
@@ -210,6 +211,7 @@ __global__ void __launch_bounds__(128 * G, 1) value_head_tc_kernel(const float* 
                 v2 = fmaf(fmaxf(__uint_as_float(d8[4 * c + 2]) + b.z, 0.f), w.z, v2); v3 = fmaf(fmaxf(__uint_as_float(d8[4 * c + 3]) + b.w, 0.f), w.w, v3);
             }
         }
+        if (tile + gridDim.x * G >= ntiles) pdl_trigger();      // last tile of this CTA: the next kernel may start its prologue
         if (valid) V[s] = ((v0 + v1) + (v2 + v3)) + bias[416];
         tc_fence_before();                               // the next tile's MMAs overwrite the accumulator columns just read
     }
@@ -228,8 +230,7 @@ static cudaError_t launch_vtc(const float* E, int B, const float* vw, float* V, 
     const int ntiles = (B + 127) / 128;
     const int want = (ntiles + G - 1) / G;
     const int grid = want < num_sms ? want : num_sms;
-    value_head_tc_kernel<G><<<grid, 128 * G, smem, st>>>(E, B, vw, V, ntiles);
-    return cudaGetLastError();
+    return launch_pdl(value_head_tc_kernel<G>, dim3(grid), dim3(128 * G), smem, st, E, B, vw, V, ntiles);
 }
 
 cudaError_t run_value_head_tc(const float* E, int B, const float* vw, float* V, int num_sms, size_t max_smem, cudaStream_t st) {
