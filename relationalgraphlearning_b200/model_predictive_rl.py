@@ -29,7 +29,7 @@ import torch
 
 from . import ops
 from .graph_model import RGL
-from .simtypes import ActionRot, ActionXY, Policy, joint_state_to_tensors
+from .simtypes import ActionRot, ActionXY, Policy, joint_state_to_tensors, joint_states_to_tensors
 from .state_predictor import LinearStatePredictor, StatePredictor
 from .value_estimator import ValueEstimator
 
@@ -362,6 +362,42 @@ class ModelPredictiveRL(Policy):
         if self.phase == 'train':
             self.last_state = self.transform(state)
         return max_action
+
+    def predict_many(self, states):
+        """Vectorised front end: predict() for MANY environments stepped together -- what
+        Explorer.run_k_episodes / Robot.act (crowd_nav/utils/explorer.py:42-53, crowd_sim/envs/utils/robot.py:9-15) do one
+        JointState at a time.  Same per-state semantics as predict(): reach_destination short-circuit, epsilon-greedy in
+        the train phase (one np.random draw per state, in order), greedy look-ahead otherwise -- but every greedy state goes
+        through ONE batched look-ahead (predict_batch).  Returns the list of actions; in the train phase `last_state`
+        becomes the list of transformed states (one per environment)."""
+        if self.phase is None or self.device is None:
+            raise AttributeError('Phase, device attributes have to be set!')
+        if self.phase == 'train' and self.epsilon is None:
+            raise AttributeError('Epsilon attribute has to be set in training phase')
+        if self.action_space is None:
+            self.build_action_space(states[0].robot_state.v_pref)
+        stop = ActionXY(0, 0) if self.kinematics == 'holonomic' else ActionRot(0, 0)
+        actions = [None] * len(states)
+        greedy = []
+        for i, st in enumerate(states):
+            if self.reach_destination(st):
+                actions[i] = stop
+                continue
+            if self.phase == 'train' and np.random.random() < self.epsilon:
+                actions[i] = self.action_space[np.random.choice(len(self.action_space))]
+            else:
+                greedy.append(i)
+        if greedy:
+            robot, humans = joint_states_to_tensors([states[i] for i in greedy], self.device)
+            best = self.predict_batch(robot, humans).cpu().tolist()
+            for i, b in zip(greedy, best):
+                if b < 0:
+                    raise ValueError('Value network is not well trained.')
+                actions[i] = self.action_space[b]
+        if self.phase == 'train':
+            robot, humans = joint_states_to_tensors(states, self.device)
+            self.last_state = [(robot[i], humans[i]) for i in range(len(states))]      # transform() of every state
+        return actions
 
     def _build_traj(self, robot, humans, det, b):
         """[(state, action, reward), ...] along the best branch, as the reference's max_traj (:231, :295-300)."""

@@ -134,3 +134,23 @@ def joint_state_to_tensors(state, device):
     robot = torch.tensor([[list(state.robot_state.to_tuple())]], dtype=torch.float32)
     humans = torch.tensor([[list(h.to_tuple()) for h in state.human_states]], dtype=torch.float32)
     return robot.to(device), humans.to(device)
+
+
+def joint_states_to_tensors(states, device):
+    """Vectorised JointState.to_tensor (state.py:64-79) for many environments that are stepped together:
+    list of JointState (equal human counts) -> (robot[E,1,9], humans[E,Nh,5]) fp32 on `device`, staged through ONE pinned
+    host buffer and one host->device copy per tensor instead of 2*E tiny tensors."""
+    E = len(states)
+    nh = len(states[0].human_states)
+    flat = np.empty((E, 9 + 5 * nh), dtype=np.float32)
+    for e, st in enumerate(states):
+        assert len(st.human_states) == nh, 'states stepped together must have the same number of humans'
+        flat[e, :9] = st.robot_state.to_tuple()
+        for h, hs in enumerate(st.human_states):
+            flat[e, 9 + 5 * h: 14 + 5 * h] = hs.to_tuple()
+    host = torch.from_numpy(flat)
+    dev = torch.device(device)
+    if dev.type == 'cuda':
+        host = host.pin_memory()
+    both = host.to(dev, non_blocking=True)
+    return both[:, :9].reshape(E, 1, 9).contiguous(), both[:, 9:].reshape(E, nh, 5).contiguous()

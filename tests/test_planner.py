@@ -282,3 +282,27 @@ def test_graphed_predict_equals_eager_and_tracks_weight_updates(cuda_device):
     # predict() uses the graphed path and still builds the trajectory
     a = pol.predict(joint_state(g['robot'], g['humans'], 0))
     assert a == pol.action_space[int(be[0])] and pol.traj[0][1] == a
+
+
+@pytest.mark.gpu
+def test_predict_many_equals_per_state_predict(cuda_device):
+    """Vectorised front end: many environments stepped together give the actions predict() gives one state at a time."""
+    g = load_golden('planner_d2w2_nh5')
+    pol = make_policy(g, cuda_device, planning_depth=2, planning_width=2, do_action_clip=True, speed_samples=2, rotation_samples=5)
+    pol.build_action_space(1.0)
+    robot, humans = synthetic_states(40, 5, seed=66)
+    robot[7, 0, 0:2] = robot[7, 0, 5:7]                       # already at the goal: short-circuit to the stop action
+    states = [joint_state(robot, humans, b) for b in range(40)]
+    many = pol.predict_many(states)
+    assert many[7] == ActionXY(0, 0)
+    for b in (0, 7, 13, 39):
+        assert pol.predict(states[b]) == many[b]
+    # train phase: epsilon-greedy per state, last_state holds every transformed state
+    pol.set_phase('train')
+    pol.set_epsilon(0.5)
+    np.random.seed(3)
+    acts = pol.predict_many(states)
+    assert len(acts) == 40 and all(a in pol.action_space for a in acts)
+    assert len(pol.last_state) == 40 and pol.last_state[5][0].shape == (1, 9) and pol.last_state[5][1].shape == (5, 5)
+    rt, ht = pol.transform(states[5])
+    assert torch.equal(pol.last_state[5][0], rt) and torch.equal(pol.last_state[5][1], ht)
