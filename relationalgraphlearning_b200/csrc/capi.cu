@@ -95,9 +95,18 @@ int rgl_graph_forward(const float* robot, const float* humans, int B, int Nh, in
     // product on the fp32 FMA pipe.  RGL_GRAPH_VARIANT (experiments only): 't' = tcgen05, anything else selects one of
     // the legacy FFMA / mma.sync variants of graph_forward.cu.
     static const char* variant = getenv("RGL_GRAPH_VARIANT");
-    const bool tc = (variant ? variant[0] == 't' : true) && !(flags & RGL_FLAG_FP32_FMA);
-    cudaError_t e = tc ? rgl::run_graph_forward_tc(a, d.sms, d.max_smem, (cudaStream_t)stream)
-                       : rgl::run_graph_forward(a, d.sms, d.max_smem, (cudaStream_t)stream);
+    const bool tc = (variant ? (variant[0] == 't' || variant[0] == 'p') : true) && !(flags & RGL_FLAG_FP32_FMA);
+    // 'p' = the row-paired tcgen05 kernel (graph_forward_tp.cu; compiled node counts n = 6, 11, 21).  Default policy from
+    // the B200 measurements (gpurun_out/r2_qt_{t,p}.log, states/s at steady state, t -> p): H 1176 -> 1234 M and S 1013 ->
+    // 1072 M at n = 6, H 307 -> 367 M, E 353 -> 389 M at n = 11; but the value path (E only), whose last layer runs for the
+    // robot rows alone, is faster on the robot-first layout of graph_forward_tc.cu at n = 6 (1321 vs 1265 M) and n = 21.
+    const bool e_only = !H && !S;
+    const bool paired = tc && (variant ? variant[0] == 'p' : (!e_only || Nh + 1 == 11));
+    cudaError_t e = cudaErrorNotSupported;
+    if (paired) e = rgl::run_graph_forward_tp(a, d.sms, d.max_smem, (cudaStream_t)stream);
+    if (e == cudaErrorNotSupported)
+        e = tc ? rgl::run_graph_forward_tc(a, d.sms, d.max_smem, (cudaStream_t)stream)
+               : rgl::run_graph_forward(a, d.sms, d.max_smem, (cudaStream_t)stream);
     if (e == cudaErrorInvalidConfiguration) return fail(RGL_EUNSUPPORTED, "rgl_graph_forward: tile does not fit in shared memory");
     return e == cudaSuccess ? RGL_OK : fail_cuda(e, "rgl_graph_forward");
 }

@@ -67,6 +67,8 @@ struct GraphArgs {
 cudaError_t run_graph_forward(const GraphArgs& a, int num_sms, size_t max_smem, cudaStream_t st);
 // tcgen05 / TMEM variant (graph_forward_tc.cu): inference only (no activation saves)
 cudaError_t run_graph_forward_tc(const GraphArgs& a, int num_sms, size_t max_smem, cudaStream_t st);
+// row-paired tcgen05 variant (graph_forward_tp.cu): n = 6, 11, 21; cudaErrorNotSupported otherwise
+cudaError_t run_graph_forward_tp(const GraphArgs& a, int num_sms, size_t max_smem, cudaStream_t st);
 cudaError_t run_value_head(const float* E, int B, const float* vw, float* V, float* v0, float* v1, float* v2, int use_tma, int num_sms,
                            cudaStream_t st);
 // tcgen05 value network (value_head_tc.cu): inference only
