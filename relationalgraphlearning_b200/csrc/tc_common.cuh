@@ -61,6 +61,29 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&r)[32], uin
         : RGL_R8(r, 0), RGL_R8(r, 8), RGL_R8(r, 16), RGL_R8(r, 24), RGL_R8(q, 0), RGL_R8(q, 8), RGL_R8(q, 16), RGL_R8(q, 24)
         : "r"(taddr), "r"(taddr + 32) : "memory");
 }
+// 16 / 8 columns (the column-sliced kernels: graph_forward_tq.cu)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : RGL_R8(r, 0), RGL_R8(r, 8) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16x2(uint32_t t0, uint32_t t1, uint32_t (&r)[16], uint32_t (&q)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%32];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%33];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : RGL_R8(r, 0), RGL_R8(r, 8), RGL_R8(q, 0), RGL_R8(q, 8) : "r"(t0), "r"(t1) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : RGL_R8(r, 0) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" :: "r"(taddr), RGL_I8(r, 0) : "memory");
+}
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
                  :: "r"(taddr), RGL_I8(r, 0), RGL_I8(r, 8) : "memory");
@@ -105,6 +128,23 @@ __device__ __forceinline__ void st_split(uint32_t t_hi, uint32_t t_lo, const flo
         tmem_st16(t_hi + b, hi);
         tmem_st16(t_lo + b, lo);
     }
+}
+
+// 8-value variant (K = 16 operand shared by two threads)
+__device__ __forceinline__ void st_split8(uint32_t t_hi, uint32_t t_lo, const float (&v)[8]) {
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        hi[j] = (__float_as_uint(v[j]) + 0x1000u) & 0xffffe000u;
+        if (j & 1) {
+            float l0, l1;
+            unpack2(sub2(pack2(v[j - 1], v[j]), pack2u(hi[j - 1], hi[j])), l0, l1);
+            lo[j - 1] = __float_as_uint(l0);
+            lo[j] = __float_as_uint(l1);
+        }
+    }
+    tmem_st8(t_hi, hi);
+    tmem_st8(t_lo, lo);
 }
 
 // one lane of a converged warp, chosen by the hardware (elect.sync): the compiler knows a single thread runs the guarded code,

@@ -17,13 +17,6 @@
 
 namespace rgl {
 
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n\t"
-        "tcgen05.wait::ld.sync.aligned;"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-        : "r"(taddr) : "memory");
-}
 
 constexpr int VT_COLS = 256;
 constexpr int VC_D = 0, VC_A0 = 128, VC_A1 = 192;      // A buffers: hi at +0, lo at +32
