@@ -7,6 +7,7 @@
 //                     per CTA and flushed with one atomicAdd per element), bias gradient; optional relu mask
 //   attn_layer_bwd    H' = relu(A H W) + H :  gH += A^T gM,  gA += gM H^T           (per state)
 //   sim_bwd           A = softmax(Y X^T):  gS, gY = gS X, gX += gS^T Y            (per state)
+#include <stdlib.h>
 #include "kernels.h"
 
 namespace rgl {
@@ -18,7 +19,10 @@ struct Rows {
     int ld;
     int rpg;
     long long gstride;
-    __device__ __forceinline__ float* row(int r) const { return ptr + (long long)(r / rpg) * gstride + (long long)(r % rpg) * ld; }
+    __device__ __forceinline__ float* row(int r) const {
+        if (rpg == 1) return ptr + (long long)r * gstride;              // plain matrix / one row per group: no division
+        return ptr + (long long)(r / rpg) * gstride + (long long)(r % rpg) * ld;
+    }
 };
 
 struct LinBwdArgs {
@@ -211,6 +215,292 @@ __global__ void __launch_bounds__(256, 2) rows_linear_bwd_kernel(const LinBwdArg
     if (a.db && tid < N) atomicAdd(a.db + tid, bacc);
 }
 
+// ---- the same layer backward on the tensor cores (warp-level mma.sync m16n8k8, 3xTF32: fp32-grade products) -------
+// The FMA kernel above spends 65 us per launch on ~10 us of HBM traffic (68 % of the C4 training step,
+// profiles/r1_launches_train_b8192_nh10.md): every tile is load -> barrier -> FMA -> barrier with nothing in flight.
+// Per tile of MROWS rows, 8 warps:
+//   data gradient    Gin[r][k] = sum_n G[r][n] W[n][k]     A = G rows, B = W; a warp owns 16 rows (and, for 64-row tiles,
+//                                                          half of the k columns)
+//   weight gradient  dW[k][n] += sum_r X[r][k] G[r][n]     (16 x 8) tiles of dW dealt round-robin to the warps, the row
+//                                                          index is the contraction: A = X^T, B = G, both read straight
+//                                                          from the row-major staging tiles (strides = 8 mod 32 words:
+//                                                          conflict-free fragment loads)
+// Staging is cp.async (16-byte, zero-filled out of range) into a DOUBLE buffer: the next tile's G / mask / X rows are in
+// flight while the current tile is multiplied; the relu mask is applied in place by the thread that copied the chunk.
+// dW / db accumulate in registers over the tiles of a persistent CTA and are flushed with one atomicAdd per element.
+//   <128, 4, true>   N, K <= 64: every layer whose row count is B*n (GCN layers, w_a, embeddings, motion head)
+//   <64, 16, false>  N, K <= 128: the 100-wide value-head layers (B rows; single buffer: the tiles fill shared memory)
+__device__ __forceinline__ void cp_async16(uint32_t dst_s, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst_s), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int NLEFT>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(NLEFT) : "memory"); }
+
+// Every shape parameter is a template argument (N8 = ceil(N/8), K16 = ceil(K/16)): the first version took them at run time
+// and spent 95 % of its instructions on index arithmetic (ncu: 2 550 warp instructions per warp and tile for 96 HMMA,
+// instruction-cache hit rate 80 %).
+template <int N8, int K16, int MROWS, bool DB>
+__global__ void __launch_bounds__(256, 1) rows_linear_bwd_mma_kernel(const LinBwdArgs a) {
+    extern __shared__ __align__(128) float smem[];
+    constexpr int NP = N8 * 8, KP = K16 * 16, K8 = K16 * 2;
+    constexpr int ldg = ((NP + 31) / 32) * 32 + 8, ldx = ((KP + 31) / 32) * 32 + 8;      // = 8 mod 32 words
+    constexpr int WPR = 8 / (MROWS / 16);   // warps sharing a 16-row block in the data gradient (1 or 2): they split the k columns
+    constexpr int KPW = (K8 + WPR - 1) / WPR;                // k column tiles per warp in the data gradient
+    constexpr int WT = K16 * N8, TW = (WT + 7) / 8;          // (16 x 8) tiles of dW; tile id = warp + 8 i
+    constexpr int tileG = MROWS * ldg, tileX = MROWS * ldx, stage_floats = 2 * tileG + tileX;
+    constexpr int n4 = NP / 4, k4 = KP / 4;
+    const int N = a.N, K = a.K;
+    float* Ws = smem;                       // [NP][ldx]   Ws[n][k]
+    float* Gs0 = Ws + NP * ldx;             // per stage: [MROWS][ldg] masked gradient | [MROWS][ldg] mask | [MROWS][ldx] layer input
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+
+    if (a.W) {
+        // 8 independent loads in flight per thread (a rolled loop would serialise one global round trip per element)
+        for (int base = tid; base < NP * ldx; base += 8 * 256) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int idx = base + 256 * u;
+                const int nn = idx / ldx, k = idx - nn * ldx;
+                v[u] = (idx < NP * ldx && nn < N && k < K) ? (a.w_layout == 0 ? a.W[(size_t)nn * K + k] : a.W[(size_t)k * N + nn]) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (base + 256 * u < NP * ldx) Ws[base + 256 * u] = v[u];
+        }
+    }
+    float wacc[TW][4];
+#pragma unroll
+    for (int i = 0; i < TW; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) wacc[i][c] = 0.f;
+    float bacc = 0.f;
+
+    // issue the copies of one tile into stage `st` (vector path: cp.async; otherwise plain loads / stores by the same thread)
+    auto stage = [&](int tile, int st) {
+        float* Gs = Gs0 + st * stage_floats;
+        float* Ms = Gs + tileG;
+        float* Xs = Ms + tileG;
+        const int r0 = tile * MROWS;
+        if (a.vecG) {
+#pragma unroll
+            for (int i = 0; i < (MROWS * n4 + 255) / 256; ++i) {
+                const int idx = tid + 256 * i;
+                const int r = idx / n4, c = (idx - r * n4) << 2;
+                if (idx < MROWS * n4) {
+                    const bool in = r0 + r < a.R && c < N;
+                    cp_async16(smem_u32(Gs + r * ldg + c), in ? a.G.row(r0 + r) + c : a.G.ptr, in ? 16u : 0u);
+                    if (a.mask.ptr) cp_async16(smem_u32(Ms + r * ldg + c), in ? a.mask.row(r0 + r) + c : a.mask.ptr, in ? 16u : 0u);
+                }
+            }
+        } else {
+            for (int idx = tid; idx < MROWS * NP; idx += 256) {
+                const int r = idx / NP, c = idx - r * NP;
+                float v = 0.f;
+                if (r0 + r < a.R && c < N) {
+                    v = a.G.row(r0 + r)[c];
+                    if (a.mask.ptr && !(a.mask.row(r0 + r)[c] > 0.f)) v = 0.f;
+                }
+                Gs[r * ldg + c] = v;
+            }
+        }
+        if (a.Xin.ptr) {
+            if (a.vecX) {
+#pragma unroll
+                for (int i = 0; i < (MROWS * k4 + 255) / 256; ++i) {
+                    const int idx = tid + 256 * i;
+                    const int r = idx / k4, c = (idx - r * k4) << 2;
+                    if (idx < MROWS * k4) {
+                        const bool in = r0 + r < a.R && c < K;
+                        cp_async16(smem_u32(Xs + r * ldx + c), in ? a.Xin.row(r0 + r) + c : a.Xin.ptr, in ? 16u : 0u);
+                    }
+                }
+            } else {
+                for (int idx = tid; idx < MROWS * KP; idx += 256) {
+                    const int r = idx / KP, c = idx - r * KP;
+                    Xs[r * ldx + c] = (r0 + r < a.R && c < K) ? a.Xin.row(r0 + r)[c] : 0.f;
+                }
+            }
+        }
+        cp_async_commit();
+    };
+
+    int it = 0;
+    if (blockIdx.x < a.ntiles) stage(blockIdx.x, 0);
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
+        const int st = DB ? (it & 1) : 0;
+        float* Gs = Gs0 + st * stage_floats;
+        float* Ms = Gs + tileG;
+        float* Xs = Ms + tileG;
+        const int r0 = tile * MROWS;
+        const int next = tile + gridDim.x;
+        if (DB && next < a.ntiles) { stage(next, st ^ 1); cp_async_wait<1>(); } else cp_async_wait<0>();
+        // relu mask, in place, by the thread that copied the chunk (its own cp.async results are visible to it)
+        if (a.vecG && a.mask.ptr) {
+#pragma unroll
+            for (int i = 0; i < (MROWS * n4 + 255) / 256; ++i) {
+                const int idx = tid + 256 * i;
+                const int r = idx / n4, c = (idx - r * n4) << 2;
+                if (idx < MROWS * n4) {
+                    float4 v = lds128(Gs + r * ldg + c);
+                    const float4 m = lds128(Ms + r * ldg + c);
+                    v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f; v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
+                    sts128(Gs + r * ldg + c, v);
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- data gradient: a warp owns 16 rows (x a share of the k columns when two warps split a row block) ----
+        if (a.W && a.Gin.ptr) {
+            const int rb = warp / WPR, part = warp - rb * WPR;
+            const int nt0 = part * KPW;
+            float acc[KPW][4];
+#pragma unroll
+            for (int nt = 0; nt < KPW; ++nt)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[nt][c] = 0.f;
+            const float* gr = Gs + (rb * 16 + g) * ldg + t;
+            const float* wr0 = Ws + t * ldx + nt0 * 8 + g;
+#pragma unroll 2
+            for (int ks = 0; ks < N8; ++ks) {
+                uint32_t ahi[4], alo[4];
+                split_tf32(gr[ks * 8], ahi[0], alo[0]);
+                split_tf32(gr[ks * 8 + 8 * ldg], ahi[1], alo[1]);
+                split_tf32(gr[ks * 8 + 4], ahi[2], alo[2]);
+                split_tf32(gr[ks * 8 + 8 * ldg + 4], ahi[3], alo[3]);
+                const float* wr = wr0 + ks * 8 * ldx;
+#pragma unroll
+                for (int nt = 0; nt < KPW; ++nt) {
+                    if (WPR == 1 || nt0 + nt < K8) {
+                        uint32_t bh0, bl0, bh1, bl1;
+                        split_tf32(wr[nt * 8], bh0, bl0);
+                        split_tf32(wr[nt * 8 + 4 * ldx], bh1, bl1);
+                        mma_tf32(acc[nt], alo, bh0, bh1);
+                        mma_tf32(acc[nt], ahi, bl0, bl1);
+                        mma_tf32(acc[nt], ahi, bh0, bh1);
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int r = r0 + rb * 16 + g + 8 * q;
+                if (r < a.R) {
+                    float* o = a.Gin.row(r) + nt0 * 8 + 2 * t;
+#pragma unroll
+                    for (int nt = 0; nt < KPW; ++nt) {
+                        const int k = (nt0 + nt) * 8 + 2 * t;
+                        if (k + 1 < K && ((reinterpret_cast<uintptr_t>(o + nt * 8) & 7u) == 0)) {
+                            float2 v = make_float2(acc[nt][2 * q], acc[nt][2 * q + 1]);
+                            if (a.accumulate) { const float2 old = *reinterpret_cast<const float2*>(o + nt * 8); v.x += old.x; v.y += old.y; }
+                            *reinterpret_cast<float2*>(o + nt * 8) = v;
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 2; ++j)
+                                if (k + j < K) o[nt * 8 + j] = a.accumulate ? o[nt * 8 + j] + acc[nt][2 * q + j] : acc[nt][2 * q + j];
+                        }
+                    }
+                }
+            }
+        }
+        // ---- weight gradient: the rows of the tile are the contraction ----
+        if (a.dW) {
+#pragma unroll
+            for (int i = 0; i < TW; ++i) {
+                const int id = warp + 8 * i;
+                if (WT % 8 == 0 || id < WT) {
+                    const int mt = id / N8, nt = id - mt * N8;
+                    const float* xp = Xs + t * ldx + mt * 16 + g;
+                    const float* gp = Gs + t * ldg + nt * 8 + g;
+                    // two accumulators: even / odd k-steps (halves the dependent HMMA chain)
+                    float w2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+                    for (int ks = 0; ks < MROWS / 8; ++ks) {
+                        uint32_t ahi[4], alo[4], bh0, bl0, bh1, bl1;
+                        split_tf32(xp[(ks * 8) * ldx], ahi[0], alo[0]);
+                        split_tf32(xp[(ks * 8) * ldx + 8], ahi[1], alo[1]);
+                        split_tf32(xp[(ks * 8 + 4) * ldx], ahi[2], alo[2]);
+                        split_tf32(xp[(ks * 8 + 4) * ldx + 8], ahi[3], alo[3]);
+                        split_tf32(gp[(ks * 8) * ldg], bh0, bl0);
+                        split_tf32(gp[(ks * 8 + 4) * ldg], bh1, bl1);
+                        if (ks & 1) {
+                            mma_tf32(w2, alo, bh0, bh1);
+                            mma_tf32(w2, ahi, bl0, bl1);
+                            mma_tf32(w2, ahi, bh0, bh1);
+                        } else {
+                            mma_tf32(wacc[i], alo, bh0, bh1);
+                            mma_tf32(wacc[i], ahi, bl0, bl1);
+                            mma_tf32(wacc[i], ahi, bh0, bh1);
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) wacc[i][c] += w2[c];
+                }
+            }
+        }
+        if (a.db && (tid & 127) < N) {
+            // column sums: both halves of the CTA take half of the rows, four independent partial sums each
+            const float* gc = Gs + (tid >> 7) * (MROWS / 2) * ldg + (tid & 127);
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 4
+            for (int r = 0; r < MROWS / 2; r += 4) {
+                s0 += gc[r * ldg]; s1 += gc[(r + 1) * ldg]; s2 += gc[(r + 2) * ldg]; s3 += gc[(r + 3) * ldg];
+            }
+            bacc += (s0 + s1) + (s2 + s3);
+        }
+        __syncthreads();                    // every warp is done with this stage before it is refilled
+        if (!DB && next < a.ntiles) stage(next, 0);
+    }
+    // ---- flush the per-CTA partial sums: accumulator fragment (m16n8): [0],[1] = row g, cols 2t, 2t+1; [2],[3] = row g+8 ----
+    if (a.dW) {
+#pragma unroll
+        for (int i = 0; i < TW; ++i) {
+            const int id = warp + 8 * i;
+            if (WT % 8 == 0 || id < WT) {
+                const int mt = id / N8, nt = id - mt * N8;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int k = mt * 16 + g + 8 * (c >> 1), nn = nt * 8 + 2 * t + (c & 1);
+                    if (k < K && nn < N) atomicAdd(a.dW + (a.w_layout == 0 ? (size_t)nn * K + k : (size_t)k * N + nn), wacc[i][c]);
+                }
+            }
+        }
+    }
+    if (a.db && (tid & 127) < N) atomicAdd(a.db + (tid & 127), bacc);
+}
+
+template <int N8, int K16, int MROWS, bool DB>
+static cudaError_t launch_bwd_mma(LinBwdArgs& a, int num_sms, size_t max_smem, cudaStream_t st) {
+    constexpr int NP = N8 * 8, KP = K16 * 16;
+    constexpr int ldg = ((NP + 31) / 32) * 32 + 8, ldx = ((KP + 31) / 32) * 32 + 8;
+    constexpr size_t stage = (size_t)2 * MROWS * ldg + (size_t)MROWS * ldx;
+    constexpr size_t sm = ((size_t)NP * ldx + stage * (DB ? 2 : 1)) * sizeof(float);
+    static_assert(sm <= 227 * 1024, "staging tiles exceed the shared memory of an SM");
+    if (sm > max_smem) return cudaErrorInvalidConfiguration;
+    if (cudaError_t e = ensure_dyn_smem(rows_linear_bwd_mma_kernel<N8, K16, MROWS, DB>, (int)max_smem)) return e;
+    a.ntiles = (a.R + MROWS - 1) / MROWS;
+    rows_linear_bwd_mma_kernel<N8, K16, MROWS, DB><<<a.ntiles < num_sms ? a.ntiles : num_sms, 256, sm, st>>>(a);
+    return cudaGetLastError();
+}
+
+// the layer shapes of the path (N8 = ceil(N/8), K16 = ceil(K/16)); cudaErrorNotSupported: no instantiation
+static cudaError_t dispatch_bwd_mma(LinBwdArgs& a, int num_sms, size_t max_smem, cudaStream_t st) {
+    const int N8 = (a.N + 7) / 8, K16 = (a.K + 15) / 16;
+#define RGL_BWD_CASE(n8, k16, rows, db) if (N8 == n8 && K16 == k16) return launch_bwd_mma<n8, k16, rows, db>(a, num_sms, max_smem, st)
+    RGL_BWD_CASE(4, 2, 128, true);      // 32 x 32: GCN layers, w_a, value layer 0
+    RGL_BWD_CASE(4, 4, 128, true);      // 32 x 64: embedding layer 2 (w_r.2, w_h.2)
+    RGL_BWD_CASE(8, 1, 128, true);      // 64 x 5 / 64 x 9: embedding layer 1 (w_h.0, w_r.0)
+    RGL_BWD_CASE(8, 2, 128, true);      // 64 x 32: motion head layer 0
+    RGL_BWD_CASE(1, 4, 128, true);      // 5 x 64: motion head layer 1
+    RGL_BWD_CASE(1, 7, 64, false);      // 1 x 100: value layer 3
+    RGL_BWD_CASE(13, 7, 64, false);     // 100 x 100: value layer 2
+    RGL_BWD_CASE(13, 2, 64, false);     // 100 x 32: value layer 1
+#undef RGL_BWD_CASE
+    return cudaErrorNotSupported;
+}
+
 // ---- layer backward through A: one thread per (state, node j) ------------------------------------------------------
 // gHprev[b,j,:] = (skip ? gH[b,j,:] : 0) + sum_i A[b,i,j] gM[b,i,:]        gA[b,i,j] (+)= gM[b,i,:] . Hprev[b,j,:]
 __global__ void attn_layer_bwd_kernel(const float* __restrict__ A, const float* __restrict__ Hprev, const float* __restrict__ gM,
@@ -319,17 +609,23 @@ cudaError_t run_linear_bwd(const RglRows* G, int N, const RglRows* mask, const R
     LinBwdArgs a;
     a.G = to_rows(G); a.mask = to_rows(mask); a.Xin = to_rows(Xin); a.Gin = to_rows(Gin);
     a.N = N; a.K = K; a.R = R; a.W = W; a.w_layout = w_layout; a.accumulate = accumulate; a.dW = dW; a.db = db;
+    auto vec_ok = [](const Rows& r, int width) {
+        return r.ptr != nullptr && (reinterpret_cast<uintptr_t>(r.ptr) & 15u) == 0 && (r.ld & 3) == 0 && (r.gstride & 3) == 0 && (width & 3) == 0;
+    };
+    a.vecG = vec_ok(a.G, N) && (a.mask.ptr == nullptr || vec_ok(a.mask, N));
+    a.vecX = vec_ok(a.Xin, K);
+    // N, K <= 64: tensor-core kernel (mma.sync 3xTF32).  RGL_BWD_VARIANT=f keeps the fp32-FMA kernel (experiments only).
+    static const char* variant = getenv("RGL_BWD_VARIANT");
+    if (!(variant && variant[0] == 'f')) {
+        const cudaError_t e = dispatch_bwd_mma(a, num_sms, max_smem, st);
+        if (e != cudaErrorNotSupported && e != cudaErrorInvalidConfiguration) return e;
+    }
     a.ntiles = (R + LT - 1) / LT;
     const int NP4 = (N + 3) & ~3, NP32 = (N + 31) & ~31, KP32 = (K + 31) & ~31;
     size_t smem = ((size_t)NP4 * (KP32 + 4) + (size_t)LT * (NP32 + 4) + (size_t)LT * (KP32 + 4)) * sizeof(float);
     if (dW && smem < 8 * 1024 * sizeof(float)) smem = 8 * 1024 * sizeof(float);      // row-split reduction scratch
     if (smem > max_smem) return cudaErrorInvalidConfiguration;
     if (cudaError_t e = ensure_dyn_smem(rows_linear_bwd_kernel, (int)max_smem)) return e;
-    auto vec_ok = [](const Rows& r, int width) {
-        return r.ptr != nullptr && (reinterpret_cast<uintptr_t>(r.ptr) & 15u) == 0 && (r.ld & 3) == 0 && (r.gstride & 3) == 0 && (width & 3) == 0;
-    };
-    a.vecG = vec_ok(a.G, N) && (a.mask.ptr == nullptr || vec_ok(a.mask, N));
-    a.vecX = vec_ok(a.Xin, K);
     // several CTAs per SM hide the global-load latency of the staging phase (the tiles are small)
     int per_sm = (int)((200 * 1024) / (smem + 1024));
     per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);      // register budget: __launch_bounds__(256, 2)

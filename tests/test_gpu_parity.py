@@ -256,7 +256,7 @@ def test_full_size_properties_c2(cuda_device):
         g1.fp32_fma = False
         # (2) the value head sees only the robot row: E from the H path equals the E-only path
         E = g1.run(robot, humans, want_E=True)['E']
-        assert torch.equal(E, H[:, 0, :])
+        assert_close_scaled(E, H[:, 0, :], REL, 'E vs H[:,0]')      # (the E-only path may run another kernel variant than the H path)
         # (3) permuting humans permutes the predicted humans and leaves V unchanged up to summation order
         hp = torch.tensor([3, 0, 4, 1, 2], device=cuda_device)
         S2 = sp((robot, humans[:, hp]), None)[1]
@@ -289,7 +289,7 @@ def test_full_size_properties_c4_c5_shapes(case, nh, B, cuda_device):
         parts = torch.cat([g1((robot[:cut], humans[:cut])), g1((robot[cut:], humans[cut:]))])
         assert_close_scaled(parts, H, REL, 'H split')
         # the value head sees only the robot row; the E-only path (last layer for the robot rows only) matches the H path
-        assert torch.equal(g1.run(robot, humans, want_E=True)['E'], H[:, 0, :])
+        assert_close_scaled(g1.run(robot, humans, want_E=True)['E'], H[:, 0, :], REL, 'E vs H[:,0]')
         # humans_bcast: every state of a group of 4 reads the humans of the group's first state
         hb = humans[::4].contiguous()
         Vb = ve.run(robot, hb, humans_bcast=4)
