@@ -241,7 +241,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // and spent 95 % of its instructions on index arithmetic (ncu: 2 550 warp instructions per warp and tile for 96 HMMA,
 // instruction-cache hit rate 80 %).
 template <int N8, int K16, int MROWS, bool DB>
-__global__ void __launch_bounds__(256, 1) rows_linear_bwd_mma_kernel(const LinBwdArgs a) {
+__global__ void __launch_bounds__(256, DB ? 2 : 1) rows_linear_bwd_mma_kernel(const LinBwdArgs a) {
     extern __shared__ __align__(128) float smem[];
     constexpr int NP = N8 * 8, KP = K16 * 16, K8 = K16 * 2;
     constexpr int ldg = ((NP + 31) / 32) * 32 + 8, ldx = ((KP + 31) / 32) * 32 + 8;      // = 8 mod 32 words
@@ -481,7 +481,10 @@ static cudaError_t launch_bwd_mma(LinBwdArgs& a, int num_sms, size_t max_smem, c
     if (sm > max_smem) return cudaErrorInvalidConfiguration;
     if (cudaError_t e = ensure_dyn_smem(rows_linear_bwd_mma_kernel<N8, K16, MROWS, DB>, (int)max_smem)) return e;
     a.ntiles = (a.R + MROWS - 1) / MROWS;
-    rows_linear_bwd_mma_kernel<N8, K16, MROWS, DB><<<a.ntiles < num_sms ? a.ntiles : num_sms, 256, sm, st>>>(a);
+    int per_sm = (int)((227 * 1024) / (sm + 1024));
+    per_sm = per_sm < 1 ? 1 : (per_sm > (DB ? 2 : 1) ? (DB ? 2 : 1) : per_sm);          // matches __launch_bounds__
+    const int cap = num_sms * per_sm;
+    rows_linear_bwd_mma_kernel<N8, K16, MROWS, DB><<<a.ntiles < cap ? a.ntiles : cap, 256, sm, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -489,11 +492,17 @@ static cudaError_t launch_bwd_mma(LinBwdArgs& a, int num_sms, size_t max_smem, c
 static cudaError_t dispatch_bwd_mma(LinBwdArgs& a, int num_sms, size_t max_smem, cudaStream_t st) {
     const int N8 = (a.N + 7) / 8, K16 = (a.K + 15) / 16;
 #define RGL_BWD_CASE(n8, k16, rows, db) if (N8 == n8 && K16 == k16) return launch_bwd_mma<n8, k16, rows, db>(a, num_sms, max_smem, st)
-    RGL_BWD_CASE(4, 2, 128, true);      // 32 x 32: GCN layers, w_a, value layer 0
-    RGL_BWD_CASE(4, 4, 128, true);      // 32 x 64: embedding layer 2 (w_r.2, w_h.2)
-    RGL_BWD_CASE(8, 1, 128, true);      // 64 x 5 / 64 x 9: embedding layer 1 (w_h.0, w_r.0)
-    RGL_BWD_CASE(8, 2, 128, true);      // 64 x 32: motion head layer 0
-    RGL_BWD_CASE(1, 4, 128, true);      // 5 x 64: motion head layer 1
+    static const char* rows_env = getenv("RGL_BWD_ROWS");          // experiments only: 128-row tiles (one CTA per SM)
+    if (rows_env && rows_env[0] == '1') {
+        RGL_BWD_CASE(4, 2, 128, true);
+        RGL_BWD_CASE(4, 4, 128, true);
+        RGL_BWD_CASE(8, 1, 128, true);
+    }
+    RGL_BWD_CASE(4, 2, 64, true);       // 32 x 32: GCN layers, w_a, value layer 0          (64-row tiles: two CTAs per SM)
+    RGL_BWD_CASE(4, 4, 64, true);       // 32 x 64: embedding layer 2 (w_r.2, w_h.2)
+    RGL_BWD_CASE(8, 1, 64, true);       // 64 x 5 / 64 x 9: embedding layer 1 (w_h.0, w_r.0)
+    RGL_BWD_CASE(8, 2, 64, true);       // 64 x 32: motion head layer 0
+    RGL_BWD_CASE(1, 4, 64, true);       // 5 x 64: motion head layer 1
     RGL_BWD_CASE(1, 7, 64, false);      // 1 x 100: value layer 3
     RGL_BWD_CASE(13, 7, 64, false);     // 100 x 100: value layer 2
     RGL_BWD_CASE(13, 2, 64, false);     // 100 x 32: value layer 1
