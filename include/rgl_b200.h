@@ -216,6 +216,12 @@ int rgl_attn_layer_bwd(const float* A, const float* Hprev, const float* gM, cons
 int rgl_sim_bwd(const float* A, const float* gA, const float* X, const float* Y, float* gY, float* gX,
                 int B, int n, rgl_stream_t stream);
 
+/* Temporal-difference loss of the value step (crowd_nav/utils/trainer.py:125-129) in one launch:
+ *   target = reward + gamma_bar * V_next;  *loss += sum_b (V - target)^2 * inv_count  (zero *loss first; inv_count = 1 / global batch
+ *   reproduces MSELoss(mean));  gV[b] = 2 (V - target) * inv_count (optional): the gradient loss.backward() hands to the value head. */
+int rgl_td_loss(const float* V, const float* reward, const float* V_next, int B, float gamma_bar, float inv_count,
+                float* loss, float* gV, rgl_stream_t stream);
+
 /* ---- GPU-resident replay memory --------------------------------------------------------------------------------
  * crowd_nav/utils/memory.py:4-28 keeps python tuples of tiny tensors and torch's DataLoader collates 6 x batch_size of
  * them per minibatch (crowd_nav/utils/trainer.py:66-67,113-114).  Here a transition is one contiguous record of

@@ -85,6 +85,8 @@ EXPORTS = {
                                        ctypes.c_void_p, c_float_p, ctypes.c_void_p, c_float_p, c_float_p, c_float_p, ctypes.c_void_p]),
     'rgl_plan_backup': (ctypes.c_int, [c_float_p, c_float_p, c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int,
                                        c_float_p, ctypes.c_void_p, ctypes.c_void_p]),
+    'rgl_td_loss': (ctypes.c_int, [c_float_p, c_float_p, c_float_p, ctypes.c_int, ctypes.c_float, ctypes.c_float, c_float_p, c_float_p,
+                                   ctypes.c_void_p]),
     # GPU-resident replay memory (csrc/replay.cu)
     'rgl_replay_record_floats': (ctypes.c_int, [ctypes.c_int]),
     'rgl_replay_push': (ctypes.c_int, [c_float_p, ctypes.c_longlong, ctypes.c_int, c_float_p, c_float_p, c_float_p, c_float_p,

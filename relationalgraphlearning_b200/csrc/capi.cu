@@ -275,6 +275,14 @@ int rgl_sim_bwd(const float* A, const float* gA, const float* X, const float* Y,
     return e == cudaSuccess ? RGL_OK : fail_cuda(e, "rgl_sim_bwd");
 }
 
+int rgl_td_loss(const float* V, const float* reward, const float* V_next, int B, float gamma_bar, float inv_count, float* loss,
+                float* gV, rgl_stream_t stream) {
+    if (B == 0) return RGL_OK;
+    if (!V || !reward || !V_next || !loss || B < 0) return fail(RGL_EINVAL, "rgl_td_loss: bad argument");
+    cudaError_t e = rgl::run_td_loss(V, reward, V_next, B, gamma_bar, inv_count, loss, gV, (cudaStream_t)stream);
+    return e == cudaSuccess ? RGL_OK : fail_cuda(e, "rgl_td_loss");
+}
+
 int rgl_replay_record_floats(int Nh) { return Nh < 1 || Nh > RGL_MAX_HUMANS ? 0 : 2 * RGL_ROBOT_DIM + 2 * RGL_HUMAN_DIM * Nh + 2; }
 
 int rgl_replay_push(float* store, long long slot, int Nh, const float* robot, const float* humans, const float* value,

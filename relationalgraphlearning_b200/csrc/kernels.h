@@ -97,6 +97,8 @@ cudaError_t run_plan_select(const float* reward, const float* V, int E, int A, f
 cudaError_t run_plan_backup(const float* v, const float* nv, const float* rew, int E, int W, float gamma_bar, int depth,
                             float* ret_best, int* best, cudaStream_t st);
 
+cudaError_t run_td_loss(const float* V, const float* reward, const float* Vnext, int B, float gamma_bar, float inv_count, float* loss,
+                        float* gV, cudaStream_t st);
 cudaError_t run_replay_gather(const float* store, const long long* idx, int B, int Nh, float* robot, float* humans, float* value,
                               float* reward, float* next_robot, float* next_humans, cudaStream_t st);
 cudaError_t run_replay_push(float* store, long long slot, int Nh, const float* robot, const float* humans, const float* value,

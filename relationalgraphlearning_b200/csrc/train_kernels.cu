@@ -603,6 +603,39 @@ __global__ void sim_bwd_kernel(const float* __restrict__ A, const float* __restr
     }
 }
 
+// ---- temporal-difference loss of the value step (crowd_nav/utils/trainer.py:125-129) in one launch ---------------------
+//   target = reward + gamma_bar * V_next        (two rounded fp32 operations, like the tensor expression :126)
+//   loss  += sum_b (V - target)^2 * inv_count   (MSELoss(mean) over the GLOBAL batch: inv_count = 1 / global batch)
+//   gV     = 2 (V - target) * inv_count         (what loss.backward() hands to the value head)
+// `loss` is accumulated with one atomicAdd per block (zero it first).
+__global__ void td_loss_kernel(const float* __restrict__ V, const float* __restrict__ reward, const float* __restrict__ Vnext, int B,
+                               float gamma_bar, float inv_count, float* __restrict__ loss, float* __restrict__ gV) {
+    __shared__ float part[8];
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    float sq = 0.f;
+    if (b < B) {
+        const float target = __fadd_rn(reward[b], __fmul_rn(gamma_bar, Vnext[b]));
+        const float d = V[b] - target;
+        sq = d * d * inv_count;
+        if (gV) gV[b] = 2.f * d * inv_count;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += part[w];
+        atomicAdd(loss, s);
+    }
+}
+
+cudaError_t run_td_loss(const float* V, const float* reward, const float* Vnext, int B, float gamma_bar, float inv_count, float* loss,
+                        float* gV, cudaStream_t st) {
+    td_loss_kernel<<<(B + 255) / 256, 256, 0, st>>>(V, reward, Vnext, B, gamma_bar, inv_count, loss, gV);
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 static Rows to_rows(const RglRows* r) {
     Rows o;

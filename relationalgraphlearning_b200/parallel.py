@@ -229,8 +229,12 @@ def dp_value_step(value_estimator, target_model, optimizer, reducer, robot, huma
     reducer.step_begin(optimizer)
     out = value_estimator((robot, humans))
     with torch.no_grad():
-        target = rewards + gamma_bar * target_model((next_robot, next_humans))
-    loss = ((out - target) ** 2).sum() / float(global_batch)
+        v_next = target_model((next_robot, next_humans))
+    if out.is_cuda:
+        from . import training
+        loss = training.td_loss(out, rewards, v_next, gamma_bar, global_batch)       # one launch: target, loss, dLoss/dV
+    else:
+        loss = ((out - (rewards + gamma_bar * v_next)) ** 2).sum() / float(global_batch)
     loss.backward()
     reducer.reduce()
     optimizer.step()

@@ -230,3 +230,31 @@ def value_forward_train(ve, robot, humans):
 
 def statepred_forward_train(sp, robot, humans, detach):
     return _StatePredTrain.apply(sp, detach, robot, humans, *sp._train_params(detach))
+
+
+class _TDLoss(torch.autograd.Function):
+    """loss = sum_b (V - (reward + gamma_bar * V_next))^2 / count in ONE launch (trainer.py:125-129; MSELoss(mean) when
+    count = the global batch); the same launch stores dLoss/dV, so backward is a scale by the incoming gradient."""
+
+    @staticmethod
+    def forward(ctx, V, reward, V_next, gamma_bar, count):
+        V, reward, V_next = ops._f32c(V), ops._f32c(reward), ops._f32c(V_next)
+        B, dev = V.numel(), V.device
+        buf = torch.zeros(1 + B, dtype=torch.float32, device=dev)          # [loss | gV]
+        with torch.cuda.device(dev):
+            rc = _lib.lib().rgl_td_loss(_lib.ptr(V), _lib.ptr(reward), _lib.ptr(V_next), B, float(gamma_bar), 1.0 / float(count),
+                                        _lib.ptr(buf), ctypes.c_void_p(buf.data_ptr() + 4), _lib.stream_ptr(dev))
+        _lib.check(rc, 'rgl_td_loss')
+        ops._count(1)
+        ctx.gV = buf[1:].view_as(V)
+        return buf[0]
+
+    @staticmethod
+    def backward(ctx, gloss):
+        return ctx.gV * gloss, None, None, None, None
+
+
+def td_loss(V, reward, V_next, gamma_bar, count):
+    """Fused TD loss of the value step (differentiable in V only; reward / V_next are treated as constants, as in the
+    data-parallel step where the target network runs under no_grad)."""
+    return _TDLoss.apply(V, reward, V_next, gamma_bar, count)

@@ -131,3 +131,22 @@ def test_state_predictor_native_backward(nh, B, detach, cuda_device):
             assert p.grad is None
         else:
             assert_close_scaled(p.grad, pg[name].grad, 2e-4, 'grad graph ' + name)
+
+
+def test_fused_td_loss_matches_torch(cuda_device):
+    """rgl_td_loss (target, MSE over the global batch and dLoss/dV in one launch) against the tensor expression of
+    crowd_nav/utils/trainer.py:125-129."""
+    from relationalgraphlearning_b200 import training
+    g = torch.Generator().manual_seed(5)
+    B = 1000
+    V = torch.randn(B, 1, generator=g).to(cuda_device).requires_grad_(True)
+    rew = (torch.rand(B, 1, generator=g) * 1.25 - 0.25).to(cuda_device)
+    vn = torch.randn(B, 1, generator=g).to(cuda_device)
+    gamma = 0.9 ** 0.25
+    loss = training.td_loss(V, rew, vn, gamma, 4 * B)               # count = global batch of a 4-rank step
+    (3.0 * loss).backward()
+    V2 = V.detach().clone().requires_grad_(True)
+    ref = ((V2 - (rew + gamma * vn)) ** 2).sum() / float(4 * B)
+    (3.0 * ref).backward()
+    assert abs(float(loss) - float(ref)) <= 1e-6 * max(1.0, abs(float(ref)))
+    assert torch.allclose(V.grad, V2.grad, rtol=1e-6, atol=1e-9)
