@@ -700,8 +700,10 @@ def main():
     d2h_gbs = 0.0
     if args.workload == 'graph':
         n = nh + 1
+        # destinations rotate through 16 pinned buffers (50 MB per rank): like the real result stream, the copies land in host
+        # DRAM, not in a last-level-cache-resident pair of buffers
         src = [torch.empty(B, n, 32, device=dev) for _ in range(2)]
-        dst = [torch.empty(B, n, 32).pin_memory() for _ in range(2)]
+        dst = [torch.empty(B, n, 32).pin_memory() for _ in range(16)]
         cs = [torch.cuda.Stream() for _ in range(2)]
         for rep in range(2):
             D.barrier()
@@ -711,7 +713,7 @@ def main():
                 s.wait_event(c0)
             for i in range(200):
                 with torch.cuda.stream(cs[i % 2]):
-                    dst[i % 2].copy_(src[i % 2], non_blocking=True)
+                    dst[i % 16].copy_(src[i % 2], non_blocking=True)
             for s in cs:
                 torch.cuda.current_stream().wait_stream(s)
             c1.record()
@@ -848,7 +850,7 @@ def main():
             d2h_used = e2e_value * (nh + 1) * 128 / 1e9
             out['e2e']['d2h_ceiling'] = {'aggregate_gbs': d2h_total, 'used_gbs': d2h_used, 'frac': d2h_used / d2h_total,
                                          'how': 'every rank copies 3.1 MB device->pinned-host buffers back to back at the same time '
-                                                '(2 streams, 200 copies): the host fabric bound of the H read-back'}
+                                                '(2 streams, 200 copies, 16 rotating destinations = 50 MB per rank): the host fabric bound of the H read-back'}
         if extra_ms[0] > 0:
             out['extra'] = {'value_path': {'call': 'ValueEstimator.forward = graph forward (E only) + value head -> V[B,1]',
                                            'value': world * B / (extra_ms[0] * 1e-3), 'e2e': world * B / (extra_ms[1] * 1e-3),

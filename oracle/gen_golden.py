@@ -240,6 +240,52 @@ def planner_tree_case(name, seed, nh, n_states, depth, width, sparse=False, spee
     print('wrote', name, 'chosen', chosen, 'kept', kept, 'traj', trajs)
 
 
+def gcn_case(name, seed, nh, n_states, batch=24, data_seed=55, layerwise=False, skip=True, num_layer=2):
+    """The model-free GCN policy (crowd_nav/policy/gcn.py + multi_human_rl.py + cadrl.py, config rgl.py): value-network
+    outputs on a batch of rotated joint states, and predict() -- all 81 action values and the chosen action -- on
+    n_states JointStates."""
+    stub_sim_deps()
+    from crowd_nav.policy.gcn import GCN
+    from crowd_sim.envs.utils.state import FullState, ObservableState, JointState
+    cfg = load_ref_config('rgl').PolicyConfig()
+    cfg.gcn.layerwise_graph, cfg.gcn.skip_connection, cfg.gcn.num_layer = layerwise, skip, num_layer
+    torch.manual_seed(seed)
+    pol = GCN()
+    pol.configure(cfg)
+    pol.set_device(torch.device('cpu'))
+    pol.set_phase('test')
+    pol.time_step = 0.25
+    with torch.no_grad():
+        pol.model.w_a.mul_(0.2); pol.model.w1.mul_(0.2)
+        if num_layer == 2:
+            pol.model.w2.mul_(0.2)
+    robot, humans = synthetic_states(max(n_states, batch), nh, seed=data_seed)
+    # value network on rotated joint states of the first `batch` synthetic states
+    joint = torch.cat([robot[:batch].expand(batch, nh, 9), humans[:batch]], dim=2)            # [batch, nh, 14]
+    rotated = torch.stack([pol.rotate(joint[b]) for b in range(batch)])                       # [batch, nh, 13]
+    with torch.no_grad():
+        values = pol.model(rotated)
+        A0 = np.array(pol.model.A, copy=True)
+        pol.model.double()
+        values64 = pol.model(rotated.double())
+        pol.model.float()
+    chosen, avals = [], []
+    with torch.no_grad():
+        for b in range(n_states):
+            r = [float(x) for x in robot[b, 0]]
+            st = JointState(FullState(*r), [ObservableState(*[float(x) for x in humans[b, h]]) for h in range(nh)])
+            act = pol.predict(st)
+            chosen.append([i for i, a in enumerate(pol.action_space) if a == act][0])
+            avals.append([float(v) for v in pol.action_values])
+    out = sd_np(pol.model.state_dict(), 'model/')
+    out.update(robot=robot.numpy(), humans=humans.numpy(), rotated=rotated.numpy(), values=values.numpy(), values64=values64.numpy(),
+               A0=A0, chosen=np.array(chosen), action_values=np.array(avals),
+               actions=np.array([[a.vx, a.vy] for a in pol.action_space], dtype=np.float64),
+               meta=np.array([seed, nh, n_states, batch, data_seed, int(layerwise), int(skip), num_layer], dtype=np.int64))
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
+    print('wrote', name, 'chosen', chosen, 'V range', float(values.min()), float(values.max()))
+
+
 SIMILARITIES = ['gaussian', 'cosine', 'cosine_softmax', 'concatenation', 'squared', 'equal_attention', 'diagonal']
 
 
@@ -261,6 +307,9 @@ def main():
     for sim in SIMILARITIES:
         forward_case('fwd_nh5_sim_' + sim, 3, 5, 16, layerwise=(sim in ('gaussian', 'squared')), scale=0.2, similarity=sim)
     planner_case('planner_d1_nh5', 0, 5, 8)
+    gcn_case('gcn_nh5', 0, 5, 6)                                  # model-free GCN policy (rgl.py)
+    gcn_case('gcn_nh5_layerwise_noskip', 1, 5, 3, layerwise=True, skip=False)
+    gcn_case('gcn_nh3_l1', 2, 3, 3, num_layer=1)
     planner_case('planner_d1_unicycle_nh5', 1, 5, 6, data_seed=78, kinematics='unicycle')     # ActionRot branch (:204,:319-321,:337-340)
     # depth > 1 look-ahead with action clipping, through the one-line-patched copy of the reference planner
     planner_tree_case('planner_d2w2_nh5', 0, 5, 6, 2, 2, speed_samples=2, rotation_samples=5)           # BASELINE C3: 11 actions

@@ -3,6 +3,7 @@ graph-model forward, value / state-predictor heads and the batched look-ahead of
 model_predictive_rl planner, behind the reference's own module / policy API.
 See DESIGN.md for the scope and INTEGRATION.md for how it plugs into the reference."""
 from .config import Config, policy_config  # noqa: F401
+from .gcn import GCN  # noqa: F401
 from .graph_model import RGL  # noqa: F401
 from .helpers import mlp  # noqa: F401
 from .model_predictive_rl import ModelPredictiveRL  # noqa: F401

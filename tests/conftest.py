@@ -19,7 +19,7 @@ def pytest_configure(config):
 def load_golden(name):
     """Golden fixture minted from the reference by oracle/gen_golden.py -> dict of tensors + state-dicts."""
     z = np.load(os.path.join(GOLDEN, name + '.npz'))
-    out = {'graph1': {}, 'value': {}, 'graph2': {}, 'motion': {}}
+    out = {'graph1': {}, 'value': {}, 'graph2': {}, 'motion': {}, 'model': {}}
     for k in z.files:
         if '/' in k:
             grp, key = k.split('/', 1)
