@@ -510,96 +510,103 @@ static cudaError_t dispatch_bwd_mma(LinBwdArgs& a, int num_sms, size_t max_smem,
     return cudaErrorNotSupported;
 }
 
-// ---- layer backward through A: one thread per (state, node j) ------------------------------------------------------
+// ---- layer backward through A: FOUR threads per (state, node j), 8 feature columns each ---------------------------
 // gHprev[b,j,:] = (skip ? gH[b,j,:] : 0) + sum_i A[b,i,j] gM[b,i,:]        gA[b,i,j] (+)= gM[b,i,:] . Hprev[b,j,:]
+// (one thread per row ran n dependent 128-byte row loads with 19 warps per SM: latency-bound, 22 us for 9 us of traffic;
+//  a quad of lanes splits the row, the dot product is closed with two shuffles)
 __global__ void attn_layer_bwd_kernel(const float* __restrict__ A, const float* __restrict__ Hprev, const float* __restrict__ gM,
                                       const float* __restrict__ gH, int skip, float* __restrict__ gHprev, float* __restrict__ gA,
                                       int accumulate_gA, int B, int n) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= B * n) return;
-    const int b = idx / n, j = idx - b * n;
-    float hp[32], acc[32];
-    const float4* hp4 = reinterpret_cast<const float4*>(Hprev + (size_t)idx * 32);
-#pragma unroll
-    for (int c = 0; c < 8; ++c) { const float4 v = hp4[c]; hp[4 * c] = v.x; hp[4 * c + 1] = v.y; hp[4 * c + 2] = v.z; hp[4 * c + 3] = v.w; }
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int q = (int)(t & 3);
+    const long long total = (long long)B * n;
+    const bool live = (t >> 2) < total;
+    const long long row = live ? (t >> 2) : total - 1;           // idle quads shadow the last row (the shuffles stay warp-wide)
+    const int b = (int)(row / n), j = (int)(row - (long long)b * n);
+    float hp[8], acc[8];
+    {
+        const float4* hp4 = reinterpret_cast<const float4*>(Hprev + row * 32 + 8 * q);
+        const float4 u = hp4[0], v = hp4[1];
+        hp[0] = u.x; hp[1] = u.y; hp[2] = u.z; hp[3] = u.w; hp[4] = v.x; hp[5] = v.y; hp[6] = v.z; hp[7] = v.w;
+    }
     if (skip) {
-        const float4* g4 = reinterpret_cast<const float4*>(gH + (size_t)idx * 32);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) { const float4 v = g4[c]; acc[4 * c] = v.x; acc[4 * c + 1] = v.y; acc[4 * c + 2] = v.z; acc[4 * c + 3] = v.w; }
+        const float4* g4 = reinterpret_cast<const float4*>(gH + row * 32 + 8 * q);
+        const float4 u = g4[0], v = g4[1];
+        acc[0] = u.x; acc[1] = u.y; acc[2] = u.z; acc[3] = u.w; acc[4] = v.x; acc[5] = v.y; acc[6] = v.z; acc[7] = v.w;
     } else {
 #pragma unroll
-        for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+        for (int c = 0; c < 8; ++c) acc[c] = 0.f;
     }
+    const float* Ab = A + (size_t)b * n * n + j;
+    const float* gMb = gM + (size_t)b * n * 32 + 8 * q;
+    float* gAb = gA + (size_t)b * n * n + j;
+#pragma unroll 4
     for (int i = 0; i < n; ++i) {
-        const float aij = A[((size_t)b * n + i) * n + j];
-        const float4* gm4 = reinterpret_cast<const float4*>(gM + ((size_t)b * n + i) * 32);
+        const float aij = Ab[i * n];
+        const float4 u = *reinterpret_cast<const float4*>(gMb + i * 32), v = *reinterpret_cast<const float4*>(gMb + i * 32 + 4);
+        const float gm[8] = {u.x, u.y, u.z, u.w, v.x, v.y, v.z, v.w};
         float d = 0.f;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const float4 v = gm4[c];
-            acc[4 * c] = fmaf(aij, v.x, acc[4 * c]); acc[4 * c + 1] = fmaf(aij, v.y, acc[4 * c + 1]);
-            acc[4 * c + 2] = fmaf(aij, v.z, acc[4 * c + 2]); acc[4 * c + 3] = fmaf(aij, v.w, acc[4 * c + 3]);
-            d = fmaf(v.x, hp[4 * c], d); d = fmaf(v.y, hp[4 * c + 1], d); d = fmaf(v.z, hp[4 * c + 2], d); d = fmaf(v.w, hp[4 * c + 3], d);
-        }
-        float* ga = gA + ((size_t)b * n + i) * n + j;
-        *ga = accumulate_gA ? *ga + d : d;
+        for (int c = 0; c < 8; ++c) { acc[c] = fmaf(aij, gm[c], acc[c]); d = fmaf(gm[c], hp[c], d); }
+        d += __shfl_xor_sync(0xffffffffu, d, 1);
+        d += __shfl_xor_sync(0xffffffffu, d, 2);
+        if (q == 0 && live) gAb[i * n] = accumulate_gA ? gAb[i * n] + d : d;
     }
-    float4* o4 = reinterpret_cast<float4*>(gHprev + (size_t)idx * 32);
-#pragma unroll
-    for (int c = 0; c < 8; ++c) o4[c] = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+    if (live) {
+        float4* o4 = reinterpret_cast<float4*>(gHprev + row * 32 + 8 * q);
+        o4[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        o4[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
 }
 
-// ---- similarity backward: A = softmax_j(Y_i . X_j) -----------------------------------------------------------------
+// ---- similarity backward: A = softmax_j(Y_i . X_j), four threads per (state, node), 8 columns each --------------------
 // gS_ij = A_ij (gA_ij - sum_k gA_ik A_ik);  gY_i = sum_j gS_ij X_j;  gX_j += sum_i gS_ij Y_i
-// one thread per (state, node); a CTA owns whole states so gS can be exchanged through shared memory.
+// a CTA owns whole states so gS can be exchanged through shared memory.
 __global__ void sim_bwd_kernel(const float* __restrict__ A, const float* __restrict__ gA, const float* __restrict__ X,
                                const float* __restrict__ Y, float* __restrict__ gY, float* __restrict__ gX, int B, int n, int spb) {
     extern __shared__ float gS[];                 // [spb][n][n]
-    const int sl = threadIdx.x / n, i = threadIdx.x - sl * n;
+    const int q = threadIdx.x & 3, r = threadIdx.x >> 2;
+    const int sl = r / n, i = r - sl * n;
     const int b = blockIdx.x * spb + sl;
     const bool active = sl < spb && b < B;
+    const size_t row = (size_t)b * n + i;
     if (active) {
-        const float* arow = A + ((size_t)b * n + i) * n;
-        const float* grow = gA + ((size_t)b * n + i) * n;
+        const float* arow = A + row * n;
+        const float* grow = gA + row * n;
         float dot = 0.f;
         for (int j = 0; j < n; ++j) dot = fmaf(grow[j], arow[j], dot);
-        float acc[32];
+        float acc[8];
 #pragma unroll
-        for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+        for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+        const float* Xb = X + (size_t)b * n * 32 + 8 * q;
+#pragma unroll 4
         for (int j = 0; j < n; ++j) {
             const float gs = arow[j] * (grow[j] - dot);
-            gS[(sl * n + i) * n + j] = gs;
-            const float4* x4 = reinterpret_cast<const float4*>(X + ((size_t)b * n + j) * 32);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const float4 v = x4[c];
-                acc[4 * c] = fmaf(gs, v.x, acc[4 * c]); acc[4 * c + 1] = fmaf(gs, v.y, acc[4 * c + 1]);
-                acc[4 * c + 2] = fmaf(gs, v.z, acc[4 * c + 2]); acc[4 * c + 3] = fmaf(gs, v.w, acc[4 * c + 3]);
-            }
+            if (q == 0) gS[(sl * n + i) * n + j] = gs;
+            const float4 u = *reinterpret_cast<const float4*>(Xb + j * 32), v = *reinterpret_cast<const float4*>(Xb + j * 32 + 4);
+            acc[0] = fmaf(gs, u.x, acc[0]); acc[1] = fmaf(gs, u.y, acc[1]); acc[2] = fmaf(gs, u.z, acc[2]); acc[3] = fmaf(gs, u.w, acc[3]);
+            acc[4] = fmaf(gs, v.x, acc[4]); acc[5] = fmaf(gs, v.y, acc[5]); acc[6] = fmaf(gs, v.z, acc[6]); acc[7] = fmaf(gs, v.w, acc[7]);
         }
-        float4* o4 = reinterpret_cast<float4*>(gY + ((size_t)b * n + i) * 32);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) o4[c] = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+        float4* o4 = reinterpret_cast<float4*>(gY + row * 32 + 8 * q);
+        o4[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        o4[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
     }
     __syncthreads();
     if (active) {
         const int j = i;
-        float4* o4 = reinterpret_cast<float4*>(gX + ((size_t)b * n + j) * 32);
-        float acc[32];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) { const float4 v = o4[c]; acc[4 * c] = v.x; acc[4 * c + 1] = v.y; acc[4 * c + 2] = v.z; acc[4 * c + 3] = v.w; }
+        float4* o4 = reinterpret_cast<float4*>(gX + row * 32 + 8 * q);
+        const float4 u0 = o4[0], v0 = o4[1];
+        float acc[8] = {u0.x, u0.y, u0.z, u0.w, v0.x, v0.y, v0.z, v0.w};
+        const float* Yb = Y + (size_t)b * n * 32 + 8 * q;
+#pragma unroll 4
         for (int ii = 0; ii < n; ++ii) {
             const float gs = gS[(sl * n + ii) * n + j];
-            const float4* y4 = reinterpret_cast<const float4*>(Y + ((size_t)b * n + ii) * 32);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const float4 v = y4[c];
-                acc[4 * c] = fmaf(gs, v.x, acc[4 * c]); acc[4 * c + 1] = fmaf(gs, v.y, acc[4 * c + 1]);
-                acc[4 * c + 2] = fmaf(gs, v.z, acc[4 * c + 2]); acc[4 * c + 3] = fmaf(gs, v.w, acc[4 * c + 3]);
-            }
+            const float4 u = *reinterpret_cast<const float4*>(Yb + ii * 32), v = *reinterpret_cast<const float4*>(Yb + ii * 32 + 4);
+            acc[0] = fmaf(gs, u.x, acc[0]); acc[1] = fmaf(gs, u.y, acc[1]); acc[2] = fmaf(gs, u.z, acc[2]); acc[3] = fmaf(gs, u.w, acc[3]);
+            acc[4] = fmaf(gs, v.x, acc[4]); acc[5] = fmaf(gs, v.y, acc[5]); acc[6] = fmaf(gs, v.z, acc[6]); acc[7] = fmaf(gs, v.w, acc[7]);
         }
-#pragma unroll
-        for (int c = 0; c < 8; ++c) o4[c] = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+        o4[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        o4[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
     }
 }
 
@@ -679,16 +686,16 @@ cudaError_t run_linear_bwd(const RglRows* G, int N, const RglRows* mask, const R
 
 cudaError_t run_attn_layer_bwd(const float* A, const float* Hprev, const float* gM, const float* gH, int skip, float* gHprev,
                                float* gA, int accumulate_gA, int B, int n, cudaStream_t st) {
-    const int total = B * n;
-    attn_layer_bwd_kernel<<<(total + 127) / 128, 128, 0, st>>>(A, Hprev, gM, gH, skip, gHprev, gA, accumulate_gA, B, n);
+    const long long threads = (long long)B * n * 4;
+    attn_layer_bwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(A, Hprev, gM, gH, skip, gHprev, gA, accumulate_gA, B, n);
     return cudaGetLastError();
 }
 
 cudaError_t run_sim_bwd(const float* A, const float* gA, const float* X, const float* Y, float* gY, float* gX, int B, int n,
                         cudaStream_t st) {
-    const int spb = 256 / n;
+    const int spb = 64 / n > 0 ? 64 / n : 1;                 // states per CTA: spb * n rows x 4 threads <= 256 (n <= 32: <= 128 threads for spb = 1)
     const int grid = (B + spb - 1) / spb;
-    sim_bwd_kernel<<<grid, spb * n, (size_t)spb * n * n * sizeof(float), st>>>(A, gA, X, Y, gY, gX, B, n, spb);
+    sim_bwd_kernel<<<grid, spb * n * 4, (size_t)spb * n * n * sizeof(float), st>>>(A, gA, X, Y, gY, gX, B, n, spb);
     return cudaGetLastError();
 }
 
