@@ -682,7 +682,7 @@ def main():
                 inflight.append(hstream.submit(robots_p[nsub % npin], humans_p[nsub % npin]))
                 nsub += 1
             if len(inflight) >= depth or (nsub >= steps and inflight):
-                checksum += float(hstream.result(inflight.pop(0)).view(-1)[0])     # the host reads every result
+                checksum += float(hstream.result_numpy(inflight.pop(0)).flat[0])     # the host reads every result
             if nsub >= steps and not inflight:
                 break
         hstream.drain()

@@ -44,9 +44,23 @@ class _PackCache(object):
     def __init__(self):
         self.key = None
         self.blob = None
+        self.vkey = None          # fast path: (_version of every parameter) + data_ptr of the first one
 
     def mark_dirty(self):
         self.key = None
+        self.vkey = None
+
+    def fresh(self, params):
+        """Cheap check used on per-batch hot paths (hostio.HostStream): True if no parameter's version counter moved since
+        the blob was packed and the first parameter still lives at the same address (optimizer steps and load_state_dict bump
+        the counters; .to(device) moves the storage)."""
+        vk = self.vkey
+        if vk is None or self.blob is None or len(vk) != len(params) + 1 or vk[0] != params[0].data_ptr():
+            return False
+        for i, p in enumerate(params):
+            if p._version != vk[i + 1]:
+                return False
+        return True
 
     def get(self, params, nfloats, pack_fn, force=False):
         key = tuple((p.data_ptr(), p._version) for p in params)
@@ -58,6 +72,7 @@ class _PackCache(object):
                 pack_fn(self.blob)
             _count(1)
             self.key = key
+        self.vkey = (params[0].data_ptr(),) + tuple(p._version for p in params)
         return self.blob
 
 
