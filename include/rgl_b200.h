@@ -50,6 +50,11 @@ extern "C" {
 #define RGL_FLAG_LAYERWISE  2         /* config.gcn.layerwise_graph  (graph_model.py:120-122) */
 #define RGL_FLAG_FP32_FMA   8         /* numerics: keep every GEMM on the fp32 FMA pipe (no 3xTF32 tensor-core split;
                                          the tensor path agrees with fp32 to ~3e-6 relative, the FMA path to ~3e-7) */
+#define RGL_FLAG_TRAIN_TC   16        /* rgl_graph_forward_train only: run the training forward on the tcgen05 kernel (Nh = 5, 10, 20).
+                                         Save layout: a1r = base of ONE [B,n,64] buffer (a1h must be a1r + 64), mh likewise
+                                         [B,n,64], M[l] receives Z_l = H_{l-1} W_l (the layer is evaluated as relu(A (H W))),
+                                         Rl[l] = relu(A Z_l), Hl[l] as usual; the backward then runs rgl_attn_layer_bwd (with
+                                         mask = Rl[l], Hprev = Z_l) BEFORE rgl_linear_bwd */
 #define RGL_FLAG_THROUGHPUT 4         /* scheduling hint: the caller keeps several independent launches in flight
                                          (multi-stream serving); prefer the two-CTAs-per-SM kernel variant */
 
@@ -209,9 +214,10 @@ int rgl_value_head_train(const float* E, int B, const float* value_packed, float
 int rgl_linear_bwd(const RglRows* G, int N, const RglRows* mask, const RglRows* Xin, int K,
                    const float* W, int w_layout, const RglRows* Gin, int accumulate,
                    float* dW, float* db, int R, rgl_stream_t stream);
-/* gHprev[b,j,:] = (skip ? gH[b,j,:] : 0) + sum_i A[b,i,j] gM[b,i,:];  gA[b,i,j] (+)= gM[b,i,:] . Hprev[b,j,:] */
+/* gHprev[b,j,:] = (skip ? gH[b,j,:] : 0) + sum_i A[b,i,j] gM[b,i,:];  gA[b,i,j] (+)= gM[b,i,:] . Hprev[b,j,:]
+ * mask (optional, [B,n,32]): gM is multiplied by (mask > 0) on load. */
 int rgl_attn_layer_bwd(const float* A, const float* Hprev, const float* gM, const float* gH, int skip,
-                       float* gHprev, float* gA, int accumulate_gA, int B, int n, rgl_stream_t stream);
+                       float* gHprev, float* gA, int accumulate_gA, int B, int n, const float* mask, rgl_stream_t stream);
 /* softmax + similarity backward: gY = gS X, gX += gS^T Y with gS = A (gA - rowsum(gA A)) */
 int rgl_sim_bwd(const float* A, const float* gA, const float* X, const float* Y, float* gY, float* gX,
                 int B, int n, rgl_stream_t stream);

@@ -207,7 +207,7 @@ int rgl_graph_forward_train(const float* robot, const float* humans, int B, int 
     if (B == 0) return RGL_OK;
     if (!robot || !humans || !graph_packed || !save) return fail(RGL_EINVAL, "rgl_graph_forward_train: null argument");
     if (flags & RGL_FLAG_LAYERWISE) return fail(RGL_EUNSUPPORTED, "rgl_graph_forward_train: layerwise graphs are not supported");
-    if (flags & ~(RGL_FLAG_SKIP | RGL_FLAG_THROUGHPUT)) return fail(RGL_EINVAL, "rgl_graph_forward_train: unknown flag");
+    if (flags & ~(RGL_FLAG_SKIP | RGL_FLAG_THROUGHPUT | RGL_FLAG_TRAIN_TC)) return fail(RGL_EINVAL, "rgl_graph_forward_train: unknown flag");
     if (B < 0 || Nh < 1 || Nh > RGL_MAX_HUMANS) return fail(RGL_EUNSUPPORTED, "rgl_graph_forward_train: bad batch / human count");
     if (num_layer < 1 || num_layer > RGL_MAX_LAYERS) return fail(RGL_EUNSUPPORTED, "rgl_graph_forward_train: num_layer out of range");
     if (!save->a1r || !save->a1h || !save->X || !save->Y || !save->A) return fail(RGL_EINVAL, "rgl_graph_forward_train: missing save buffer");
@@ -224,6 +224,17 @@ int rgl_graph_forward_train(const float* robot, const float* humans, int B, int 
     a.gw = graph_packed; a.mw = S ? motion_packed : nullptr; a.L = num_layer; a.flags = flags;
     a.H = H; a.E = E; a.S = S; a.A0 = nullptr; a.ntiles = 0; a.save = 1; a.sv = *save;
     a.use_tma = (aligned16(robot) && aligned16(humans)) ? 1 : 0;
+    if (flags & RGL_FLAG_TRAIN_TC) {
+        // tcgen05 training forward (graph_forward_tp.cu): hidden activations in ONE [B,n,64] buffer, M[l] = H_{l-1} W_l
+        if (save->a1h != save->a1r + RGL_EMB_HIDDEN) return fail(RGL_EINVAL, "rgl_graph_forward_train: TC layout needs a1h == a1r + 64 ([B,n,64] buffer)");
+        if (S && !save->mh) return fail(RGL_EINVAL, "rgl_graph_forward_train: S needs the mh save buffer");
+        a.save = 2;
+        a.flags = flags & ~RGL_FLAG_TRAIN_TC;
+        cudaError_t e2 = rgl::run_graph_forward_tp(a, d.sms, d.max_smem, (cudaStream_t)stream);
+        if (e2 == cudaErrorNotSupported) return fail(RGL_EUNSUPPORTED, "rgl_graph_forward_train: RGL_FLAG_TRAIN_TC covers Nh = 5, 10, 20");
+        if (e2 == cudaErrorInvalidConfiguration) return fail(RGL_EUNSUPPORTED, "rgl_graph_forward_train: tile does not fit in shared memory");
+        return e2 == cudaSuccess ? RGL_OK : fail_cuda(e2, "rgl_graph_forward_train");
+    }
     cudaError_t e = rgl::run_graph_forward(a, d.sms, d.max_smem, (cudaStream_t)stream);
     if (e == cudaErrorInvalidConfiguration) return fail(RGL_EUNSUPPORTED, "rgl_graph_forward_train: tile does not fit in shared memory");
     return e == cudaSuccess ? RGL_OK : fail_cuda(e, "rgl_graph_forward_train");
@@ -256,13 +267,13 @@ int rgl_linear_bwd(const RglRows* G, int N, const RglRows* mask, const RglRows* 
 }
 
 int rgl_attn_layer_bwd(const float* A, const float* Hprev, const float* gM, const float* gH, int skip, float* gHprev, float* gA,
-                       int accumulate_gA, int B, int n, rgl_stream_t stream) {
+                       int accumulate_gA, int B, int n, const float* mask, rgl_stream_t stream) {
     if (B == 0) return RGL_OK;
     if (!A || !Hprev || !gM || !gHprev || !gA || (skip && !gH) || B < 0 || n < 1 || n > 32)
         return fail(RGL_EINVAL, "rgl_attn_layer_bwd: bad argument");
-    if (!aligned16(Hprev) || !aligned16(gM) || !aligned16(gHprev) || (gH && !aligned16(gH)))
+    if (!aligned16(Hprev) || !aligned16(gM) || !aligned16(gHprev) || (gH && !aligned16(gH)) || (mask && !aligned16(mask)))
         return fail(RGL_EALIGN, "rgl_attn_layer_bwd: row buffers must be 16-byte aligned");
-    cudaError_t e = rgl::run_attn_layer_bwd(A, Hprev, gM, gH, skip, gHprev, gA, accumulate_gA, B, n, (cudaStream_t)stream);
+    cudaError_t e = rgl::run_attn_layer_bwd(A, Hprev, gM, gH, skip, gHprev, gA, accumulate_gA, B, n, mask, (cudaStream_t)stream);
     return e == cudaSuccess ? RGL_OK : fail_cuda(e, "rgl_attn_layer_bwd");
 }
 

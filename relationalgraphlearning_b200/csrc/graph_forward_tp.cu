@@ -38,6 +38,12 @@ __device__ __forceinline__ void xf_store_row(uint32_t rp, const float (&v)[32]) 
     for (int c = 0; c < 8; ++c) sts128s(rp + c * 16, make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
 }
 
+// training forward (a.save): this thread's node row of an activation, 32 floats -> dst (row-major [B*n][32])
+__device__ __forceinline__ void save_row32(float* dst, const float (&v)[32]) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) *reinterpret_cast<float4*>(dst + 4 * c) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+}
+
 // ---- optional phase trace (tools/trace_tc.cu builds this file with -DRGL_TC_TRACE): cycles between the marks below, summed
 // over every tile of group 0 of every CTA by a non-issuing thread (lane 0 of the group's second warp) ----
 #ifdef RGL_TC_TRACE
@@ -53,7 +59,7 @@ void tp_trace_reset() { unsigned long long z[32] = {}; cudaMemcpyToSymbol(g_tp_t
 constexpr int TC_COLS = 128;          // TMEM columns per group: [0,64) accumulators, [64,96) A hi, [96,128) A lo
 constexpr int C_D = 0, C_AHI = 64, C_ALO = 96;
 
-template <int N, int G>
+template <int N, int G, bool SAVE>
 __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tp_kernel(const GraphArgs a, const __grid_constant__ CUtensorMap mapH,
                                                                                      const int tma_out) {
     static_assert(N >= 2, "the paired kernel is instantiated for compile-time node counts");
@@ -164,6 +170,8 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tp_kern
         const long s0 = (long)tile * SPT;
         const int cnt = (int)min((long)SPT, (long)a.B - s0);
         const bool valid = row_used && s_loc < cnt;
+        const long grow = (s0 + s_loc) * n + node;           // this thread's row of the [B, n, .] activation tensors (training saves)
+        const bool saving = SAVE && valid;                   // training forward: activation saves (compile-time: the inference kernels carry none of it)
         if (tma_out && gt == 0) tma_store_wait_read();      // the previous tile's tensor stores have read the staging rows
 #ifdef RGL_TC_TRACE
         tprev = clock64();
@@ -204,6 +212,7 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tp_kern
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(__uint_as_float(h0[j]), 0.f);
+            if (saving) save_row32(a.sv.a1r + grow * 64, v);            // relu(hidden) [B, n, 64], columns 0-31
             st_split<32>(tl + C_AHI, tl + C_ALO, v);
             publish();
             TC_MARK(2);   // after: publish()
@@ -218,6 +227,7 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tp_kern
             }
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(__uint_as_float(h1[j]), 0.f);
+            if (saving) save_row32(a.sv.a1r + grow * 64 + 32, v);       // columns 32-63
             mma_wait();                      // first half consumed: its A columns may be overwritten
             TC_MARK(3);   // after: mma_wait()
             st_split<32>(tl + C_AHI, tl + C_ALO, v);
@@ -246,6 +256,7 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tp_kern
             }
         }
         xf_store_row(my_row, x);             // feature rows for the neighbours' similarity logits
+        if (saving) save_row32(a.sv.X + grow * 32, x);
 
         // ================= GCN layers: H' = relu(A (H W_l)) (+ H) =================
         // (the reference evaluates (A H) W_l; the products are reassociated so that H W_l shares its A operand with Y = H w_a)
@@ -256,7 +267,7 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tp_kern
         const uint32_t half_off = odd ? 64u : 0u;        // byte offset of this thread's column half inside a feature row
         for (int l = 0; l < a.L; ++l) {
             const bool last = (l == a.L - 1);
-            const bool robot_only = last && a.H == nullptr && a.S == nullptr;
+            const bool robot_only = last && a.H == nullptr && a.S == nullptr && !SAVE;
             const bool sim = (l == 0) || layerwise;
 
             st_split<32>(tl + C_AHI, tl + C_ALO, x);
@@ -286,6 +297,12 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tp_kern
                 {
                     uint32_t yr[32];
                     tmem_ld32(tl + C_D, yr);
+                    if (saving && l == 0) {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            *reinterpret_cast<float4*>(a.sv.Y + grow * 32 + 4 * c) = make_float4(__uint_as_float(yr[4 * c]), __uint_as_float(yr[4 * c + 1]),
+                                                                                                   __uint_as_float(yr[4 * c + 2]), __uint_as_float(yr[4 * c + 3]));
+                    }
                     // own row's Y at my half / partner row's Y at my half (the partner sends the half it does not use itself)
                     f32x2 ya[8], yb[8];
 #pragma unroll
@@ -329,6 +346,10 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tp_kern
 #pragma unroll
                         for (int j = 0; j < N; ++j) a.A0[node * n + j] = p[j];
                     }
+                    if (saving && l == 0) {
+#pragma unroll
+                        for (int j = 0; j < N; ++j) a.sv.A[grow * n + j] = p[j];
+                    }
                 }
                 group_sync();                                // every read of the feature rows is done
                 TC_MARK(8);   // after: group_sync()
@@ -339,9 +360,12 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tp_kern
                 uint32_t hw[32];
                 tmem_ld32(tl + C_D + 32, hw);
 #pragma unroll
-                for (int c = 0; c < 8; ++c)
-                    sts128s(my_row + c * 16, make_float4(__uint_as_float(hw[4 * c]), __uint_as_float(hw[4 * c + 1]),
-                                                           __uint_as_float(hw[4 * c + 2]), __uint_as_float(hw[4 * c + 3])));
+                for (int c = 0; c < 8; ++c) {
+                    const float4 v4 = make_float4(__uint_as_float(hw[4 * c]), __uint_as_float(hw[4 * c + 1]), __uint_as_float(hw[4 * c + 2]),
+                                                  __uint_as_float(hw[4 * c + 3]));
+                    sts128s(my_row + c * 16, v4);
+                    if (saving) *reinterpret_cast<float4*>(a.sv.M[l] + grow * 32 + 4 * c) = v4;      // Z_l = H_{l-1} W_l (reassociated layer)
+                }
             }
             tc_fence_before();
             group_sync();
@@ -377,6 +401,10 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tp_kern
                     const float r0_ = __shfl_xor_sync(pmask, s0_, 1), r1_ = __shfl_xor_sync(pmask, s1_, 1);
                     const float lo0 = odd ? r0_ : m0, lo1 = odd ? r1_ : m1;       // columns 2c, 2c+1
                     const float hi0 = odd ? m0 : r0_, hi1 = odd ? m1 : r1_;       // columns 16+2c, 17+2c
+                    if (saving) {            // relu(A Z_l) before the skip add (the relu mask of the backward)
+                        *reinterpret_cast<float2*>(a.sv.Rl[l] + grow * 32 + 2 * c) = make_float2(fmaxf(lo0, 0.f), fmaxf(lo1, 0.f));
+                        *reinterpret_cast<float2*>(a.sv.Rl[l] + grow * 32 + 16 + 2 * c) = make_float2(fmaxf(hi0, 0.f), fmaxf(hi1, 0.f));
+                    }
                     if (skip) {
                         x[2 * c] += fmaxf(lo0, 0.f); x[2 * c + 1] += fmaxf(lo1, 0.f);
                         x[16 + 2 * c] += fmaxf(hi0, 0.f); x[17 + 2 * c] += fmaxf(hi1, 0.f);
@@ -386,6 +414,7 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tp_kern
                     }
                 }
             }
+            if (saving) save_row32(a.sv.Hl[l] + grow * 32, x);
             if (!last && layerwise) {                        // the next layer's similarity needs the new feature rows
                 group_sync();
                 TC_MARK(10);   // after: group_sync()
@@ -428,8 +457,11 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tp_kern
                 const float4 b = lds128(tm + TM_B0 + 4 * k4);
                 const uint32_t* hh = k4 < 8 ? h0 : h1;
                 const int o = (k4 & 7) * 4;
-                const f32x2 v01 = pack2(fmaxf(__uint_as_float(hh[o + 0]) + b.x, 0.f), fmaxf(__uint_as_float(hh[o + 1]) + b.y, 0.f));
-                const f32x2 v23 = pack2(fmaxf(__uint_as_float(hh[o + 2]) + b.z, 0.f), fmaxf(__uint_as_float(hh[o + 3]) + b.w, 0.f));
+                const float m0_ = fmaxf(__uint_as_float(hh[o + 0]) + b.x, 0.f), m1_ = fmaxf(__uint_as_float(hh[o + 1]) + b.y, 0.f);
+                const float m2_ = fmaxf(__uint_as_float(hh[o + 2]) + b.z, 0.f), m3_ = fmaxf(__uint_as_float(hh[o + 3]) + b.w, 0.f);
+                if (saving && a.sv.mh) *reinterpret_cast<float4*>(a.sv.mh + grow * 64 + 4 * k4) = make_float4(m0_, m1_, m2_, m3_);   // [B, n, 64]
+                const f32x2 v01 = pack2(m0_, m1_);
+                const f32x2 v23 = pack2(m2_, m3_);
 #pragma unroll
                 for (int c = 0; c < HD; ++c) {
                     f32x2 wlo, whi;
@@ -499,14 +531,14 @@ static size_t tp_smem_bytes(int L, bool motion, int G) {
     return 1024 + ((size_t)tc_graph_floats(L) + (motion ? TMOTION_FLOATS : 0) + (size_t)G * (XF_GROUP / 4)) * 4 + (2 + G) * 8 + 16;
 }
 
-template <int N, int G>
+template <int N, int G, bool SAVE>
 static cudaError_t launch_tp(const GraphArgs& a, int num_sms, size_t max_smem, cudaStream_t st) {
     const size_t smem = tp_smem_bytes(a.L, a.mw != nullptr, G);
     if (smem > max_smem) return cudaErrorInvalidConfiguration;
     GraphArgs b = a;
     constexpr int spt = 128 / ((N + 1) & ~1);
     b.ntiles = (a.B + spt - 1) / spt;
-    if (cudaError_t e = ensure_dyn_smem(graph_forward_tp_kernel<N, G>, (int)max_smem)) return e;
+    if (cudaError_t e = ensure_dyn_smem(graph_forward_tp_kernel<N, G, SAVE>, (int)max_smem)) return e;
     int per_sm = (int)((228 * 1024) / (smem + 1024));
     const int max_cta = G <= 2 ? 2 : 1;                       // matches __launch_bounds__ and the 512 TMEM columns of an SM
     if (per_sm > max_cta) per_sm = max_cta;
@@ -519,7 +551,7 @@ static cudaError_t launch_tp(const GraphArgs& a, int num_sms, size_t max_smem, c
     memset(&mh, 0, sizeof(mh));
     int tma_out = 0;
     if (a.H != nullptr && !(tma_env && tma_env[0] == '0')) tma_out = make_state_map(&mh, a.H, a.B, N, N, spt) ? 1 : 0;
-    return launch_pdl(graph_forward_tp_kernel<N, G>, dim3(grid), dim3(128 * G), smem, st, b, mh, tma_out);
+    return launch_pdl(graph_forward_tp_kernel<N, G, SAVE>, dim3(grid), dim3(128 * G), smem, st, b, mh, tma_out);
 }
 
 template <int N>
@@ -528,14 +560,16 @@ static cudaError_t dispatch_tp(const GraphArgs& a, int num_sms, size_t max_smem,
     static const char* force = getenv("RGL_TC_GROUPS");
     constexpr int spt = 128 / ((N + 1) & ~1);
     const int ntiles = (a.B + spt - 1) / spt;
+    if (a.save)         // training forward with activation saves (TC layout: kernels.h GraphArgs::save == 2)
+        return ntiles <= 2 * num_sms ? launch_tp<N, 1, true>(a, num_sms, max_smem, st) : launch_tp<N, 2, true>(a, num_sms, max_smem, st);
     int g = force ? atoi(force) : 0;
     if (g != 1 && g != 2 && g != 4) {
         if (a.mw != nullptr) g = ntiles <= 2 * num_sms ? 1 : 4;
         else g = (ntiles <= 2 * num_sms && !(a.flags & RGL_FLAG_THROUGHPUT)) ? 1 : 2;
     }
-    if (g == 1) return launch_tp<N, 1>(a, num_sms, max_smem, st);
-    if (g == 2) return launch_tp<N, 2>(a, num_sms, max_smem, st);
-    return launch_tp<N, 4>(a, num_sms, max_smem, st);
+    if (g == 1) return launch_tp<N, 1, false>(a, num_sms, max_smem, st);
+    if (g == 2) return launch_tp<N, 2, false>(a, num_sms, max_smem, st);
+    return launch_tp<N, 4, false>(a, num_sms, max_smem, st);
 }
 
 // Node counts with a compile-time instantiation (Nh = 5, 10, 20: the BASELINE configurations); everything else runs on

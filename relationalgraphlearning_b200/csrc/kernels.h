@@ -60,7 +60,8 @@ struct GraphArgs {
     float* A0;
     int ntiles;
     int use_tma;
-    int save;                 // 1 = sv holds pointers (training forward); disables the robot-row-only last layer
+    int save;                 // 1 = sv holds pointers (training forward, fp32-FMA kernel); 2 = tcgen05 training forward (TC save layout,
+                              // include/rgl_b200.h RGL_FLAG_TRAIN_TC); disables the robot-row-only last layer
     GraphSave sv;
 };
 
@@ -77,7 +78,7 @@ cudaError_t run_linear_bwd(const RglRows* G, int N, const RglRows* mask, const R
                            const RglRows* Gin, int accumulate, float* dW, float* db, int R, int num_sms, size_t max_smem,
                            cudaStream_t st);
 cudaError_t run_attn_layer_bwd(const float* A, const float* Hprev, const float* gM, const float* gH, int skip, float* gHprev,
-                               float* gA, int accumulate_gA, int B, int n, cudaStream_t st);
+                               float* gA, int accumulate_gA, int B, int n, const float* mask, cudaStream_t st);
 cudaError_t run_sim_bwd(const float* A, const float* gA, const float* X, const float* Y, float* gY, float* gX, int B, int n,
                         cudaStream_t st);
 cudaError_t run_gcn_layer(const float* X, const float* A, const float* W, const float* wa, int B, int n, int flags,

@@ -514,9 +514,11 @@ static cudaError_t dispatch_bwd_mma(LinBwdArgs& a, int num_sms, size_t max_smem,
 // gHprev[b,j,:] = (skip ? gH[b,j,:] : 0) + sum_i A[b,i,j] gM[b,i,:]        gA[b,i,j] (+)= gM[b,i,:] . Hprev[b,j,:]
 // (one thread per row ran n dependent 128-byte row loads with 19 warps per SM: latency-bound, 22 us for 9 us of traffic;
 //  a quad of lanes splits the row, the dot product is closed with two shuffles)
+// mask (optional, [B,n,32]): gM is multiplied by (mask > 0) on load -- the relu mask of the reassociated layer
+// H' = relu(A (H W)), where this kernel runs FIRST (gM = gH', Hprev = H W) and the linear backward second.
 __global__ void attn_layer_bwd_kernel(const float* __restrict__ A, const float* __restrict__ Hprev, const float* __restrict__ gM,
                                       const float* __restrict__ gH, int skip, float* __restrict__ gHprev, float* __restrict__ gA,
-                                      int accumulate_gA, int B, int n) {
+                                      int accumulate_gA, int B, int n, const float* __restrict__ mask) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int q = (int)(t & 3);
     const long long total = (long long)B * n;
@@ -539,12 +541,19 @@ __global__ void attn_layer_bwd_kernel(const float* __restrict__ A, const float* 
     }
     const float* Ab = A + (size_t)b * n * n + j;
     const float* gMb = gM + (size_t)b * n * 32 + 8 * q;
+    const float* mkb = mask ? mask + (size_t)b * n * 32 + 8 * q : nullptr;
     float* gAb = gA + (size_t)b * n * n + j;
 #pragma unroll 4
     for (int i = 0; i < n; ++i) {
         const float aij = Ab[i * n];
         const float4 u = *reinterpret_cast<const float4*>(gMb + i * 32), v = *reinterpret_cast<const float4*>(gMb + i * 32 + 4);
-        const float gm[8] = {u.x, u.y, u.z, u.w, v.x, v.y, v.z, v.w};
+        float gm[8] = {u.x, u.y, u.z, u.w, v.x, v.y, v.z, v.w};
+        if (mkb) {
+            const float4 mu = *reinterpret_cast<const float4*>(mkb + i * 32), mv = *reinterpret_cast<const float4*>(mkb + i * 32 + 4);
+            const float mk[8] = {mu.x, mu.y, mu.z, mu.w, mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+            for (int c = 0; c < 8; ++c) gm[c] = mk[c] > 0.f ? gm[c] : 0.f;
+        }
         float d = 0.f;
 #pragma unroll
         for (int c = 0; c < 8; ++c) { acc[c] = fmaf(aij, gm[c], acc[c]); d = fmaf(gm[c], hp[c], d); }
@@ -685,9 +694,9 @@ cudaError_t run_linear_bwd(const RglRows* G, int N, const RglRows* mask, const R
 }
 
 cudaError_t run_attn_layer_bwd(const float* A, const float* Hprev, const float* gM, const float* gH, int skip, float* gHprev,
-                               float* gA, int accumulate_gA, int B, int n, cudaStream_t st) {
+                               float* gA, int accumulate_gA, int B, int n, const float* mask, cudaStream_t st) {
     const long long threads = (long long)B * n * 4;
-    attn_layer_bwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(A, Hprev, gM, gH, skip, gHprev, gA, accumulate_gA, B, n);
+    attn_layer_bwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(A, Hprev, gM, gH, skip, gHprev, gA, accumulate_gA, B, n, mask);
     return cudaGetLastError();
 }
 

@@ -8,7 +8,8 @@ as inference, additionally writing the activations the backward needs; backward 
 
   value head    4 x rgl_linear_bwd                    (gV -> gE, dW/db of the 4 Linear layers)
   motion head   2 x rgl_linear_bwd                    (gS -> gH_L on the human rows)
-  per layer     rgl_linear_bwd (W_l, relu mask)  ->  rgl_attn_layer_bwd (A^T gM, gA += gM H^T)
+  per layer     rgl_linear_bwd (W_l, relu mask)  ->  rgl_attn_layer_bwd (A^T gM, gA += gM H^T)          [fp32-FMA forward]
+                rgl_attn_layer_bwd (relu mask, Z_l)  ->  rgl_linear_bwd (W_l)                      [tcgen05 forward: relu(A (H W))]
   similarity    rgl_sim_bwd (softmax + Y X^T)    ->  rgl_linear_bwd (w_a)
   embedding     2 x rgl_linear_bwd per agent kind (robot rows / human rows of the [B,n,32] gradient, grouped-row view)
 """
@@ -49,32 +50,67 @@ def _carve(sizes, dev, zero=False):
     return views
 
 
+def _train_tc(n):
+    """The training forward runs on the tcgen05 kernel (graph_forward_tp.cu, RGL_FLAG_TRAIN_TC) for the compiled node counts;
+    RGL_TRAIN_VARIANT=f keeps the fp32-FMA kernel (experiments only)."""
+    import os
+    return n in (6, 11, 21) and os.environ.get('RGL_TRAIN_VARIANT', 't')[0] != 'f'
+
+
 def _graph_forward_train(g, robot, humans, extra_sizes, motion_blob=None, want_E=False, want_S=False):
-    """Fused graph forward with saves.  Returns (saves dict, extra views, E or None, S or None)."""
+    """Fused graph forward with saves.  Returns (saves dict, extra views, E or None, S or None).
+
+    Two save layouts (sv['tc']):
+      fp32-FMA kernel   a1r [B,64], a1h [B,Nh,64], M_l = A H_{l-1}, mh [B,Nh,64]         layer = relu((A H) W)
+      tcgen05 kernel    a1 [B,n,64] (robot row 0, humans rows 1..Nh), M_l = Z_l = H_{l-1} W_l, mh [B,n,64]   layer = relu(A (H W))
+    sv['a1r'] / sv['a1h'] / sv['mh'] are RglRows views, so the backward addresses either layout the same way."""
     B, Nh = robot.size(0), humans.size(1)
     n, L, dev = Nh + 1, g.num_layer, robot.device
-    sizes = [B * 64, B * Nh * 64, B * n * 32, B * n * 32, B * n * n] + [B * n * 32] * (3 * L) + \
-            [B * 32 if want_E else 0, B * Nh * 5 if want_S else 0, B * Nh * 64 if want_S else 0] + list(extra_sizes)
+    tc = _train_tc(n)
+    hid = [B * n * 64, 0] if tc else [B * 64, B * Nh * 64]
+    sizes = hid + [B * n * 32, B * n * 32, B * n * n] + [B * n * 32] * (3 * L) + \
+        [B * 32 if want_E else 0, B * Nh * 5 if want_S else 0, (B * n * 64 if tc else B * Nh * 64) if want_S else 0] + list(extra_sizes)
     v = _carve(sizes, dev)
-    sv = dict(a1r=v[0].view(B, 64), a1h=v[1].view(B, Nh, 64), X=v[2].view(B, n, 32), Y=v[3].view(B, n, 32), A=v[4].view(B, n, n),
+    sv = dict(tc=tc, X=v[2].view(B, n, 32), Y=v[3].view(B, n, 32), A=v[4].view(B, n, n),
               M=[v[5 + l].view(B, n, 32) for l in range(L)], Rl=[v[5 + L + l].view(B, n, 32) for l in range(L)],
               Hl=[v[5 + 2 * L + l].view(B, n, 32) for l in range(L)])
     E = v[5 + 3 * L].view(B, 32) if want_E else None
     S = v[6 + 3 * L].view(B, Nh, 5) if want_S else None
-    sv['mh'] = v[7 + 3 * L].view(B, Nh, 64) if want_S else None
+    mh = v[7 + 3 * L] if want_S else None
+    sv['_keep'] = (v[0], v[1], mh)
+    if tc:
+        sv['a1r'] = _rows(v[0], 64, 1, n * 64)                         # row 0 of every state
+        sv['a1h'] = _rows(v[0], 64, Nh, n * 64, offset=64)             # rows 1..Nh
+        sv['mh'] = _rows(mh, 64, Nh, n * 64, offset=64) if want_S else None
+        a1r_ptr, a1h_ptr = v[0].data_ptr(), v[0].data_ptr() + 64 * 4
+    else:
+        sv['a1r'] = _rows(v[0], 64)
+        sv['a1h'] = _rows(v[1], 64)
+        sv['mh'] = _rows(mh, 64) if want_S else None
+        a1r_ptr, a1h_ptr = v[0].data_ptr(), v[1].data_ptr()
     cs = _lib.GraphSave()
-    for k in ('a1r', 'a1h', 'X', 'Y', 'A'):
+    cs.a1r, cs.a1h = a1r_ptr, a1h_ptr
+    for k in ('X', 'Y', 'A'):
         setattr(cs, k, sv[k].data_ptr())
     for l in range(L):
         cs.M[l], cs.Rl[l], cs.Hl[l] = sv['M'][l].data_ptr(), sv['Rl'][l].data_ptr(), sv['Hl'][l].data_ptr()
-    cs.mh = sv['mh'].data_ptr() if want_S else None
+    cs.mh = mh.data_ptr() if want_S else None
+    flags = (g.flags() & ~_lib.FLAG_FP32_FMA) | (_lib.FLAG_TRAIN_TC if tc else 0)
     with torch.cuda.device(dev):
-        rc = _lib.lib().rgl_graph_forward_train(_lib.ptr(robot), _lib.ptr(humans), B, Nh, _lib.ptr(ops.packed_graph(g, force=ops.capturing())), L, g.flags() & ~_lib.FLAG_FP32_FMA,
+        rc = _lib.lib().rgl_graph_forward_train(_lib.ptr(robot), _lib.ptr(humans), B, Nh, _lib.ptr(ops.packed_graph(g, force=ops.capturing())), L, flags,
                                                 _lib.ptr(motion_blob) if want_S else None, ctypes.byref(cs), None,
                                                 _lib.ptr(E), _lib.ptr(S), _lib.stream_ptr(dev))
     _lib.check(rc, 'rgl_graph_forward_train')
     ops._count(1)
     return sv, v[8 + 3 * L:], E, S
+
+
+def _attn_bwd(A, Hprev, gM, gH, skip, gHprev, gA, accumulate_gA, B, n, dev, mask=None):
+    rc = _lib.lib().rgl_attn_layer_bwd(_lib.ptr(A), _lib.ptr(Hprev), _lib.ptr(gM), _lib.ptr(gH) if gH is not None else None, 1 if skip else 0,
+                                       _lib.ptr(gHprev), _lib.ptr(gA), 1 if accumulate_gA else 0, B, n,
+                                       _lib.ptr(mask) if mask is not None else None, _lib.stream_ptr(dev))
+    _lib.check(rc, 'rgl_attn_layer_bwd')
+    ops._count(1)
 
 
 def _graph_backward(g, sv, robot, humans, gH, G, dev):
@@ -88,13 +124,19 @@ def _graph_backward(g, sv, robot, humans, gH, G, dev):
     gA, gM, gY, ga_r, ga_h = t[0].view(B, n, n), t[1].view(B, n, 32), t[2].view(B, n, 32), t[3].view(B, 64), t[4].view(B * Nh, 64)
     for l in range(L - 1, -1, -1):
         Hprev = sv['X'] if l == 0 else sv['Hl'][l - 1]
-        _linear_bwd(_rows(gH, 32), 32, _rows(sv['M'][l], 32), 32, B * n, W=g.Ws[l], w_layout=1, mask=_rows(sv['Rl'][l], 32),
-                    Gin=_rows(gM, 32), dW=G(g.Ws[l]), dev=dev)
         gHp = t[5 + l].view(B, n, 32)
-        rc = lib.rgl_attn_layer_bwd(_lib.ptr(sv['A']), _lib.ptr(Hprev), _lib.ptr(gM), _lib.ptr(gH), 1 if skip else 0,
-                                    _lib.ptr(gHp), _lib.ptr(gA), 0 if l == L - 1 else 1, B, n, _lib.stream_ptr(dev))
-        _lib.check(rc, 'rgl_attn_layer_bwd')
-        ops._count(1)
+        if sv['tc']:
+            # H_l = relu(A Z) (+ H_{l-1}), Z = H_{l-1} W_l:   gZ = A^T (gH . mask),  gA (+)= (gH . mask) Z^T,
+            #                                                 dW_l = H_{l-1}^T gZ,    gH_{l-1} = gZ W_l^T (+ gH)
+            _attn_bwd(sv['A'], sv['M'][l], gH, None, False, gM, gA, l != L - 1, B, n, dev, mask=sv['Rl'][l])
+            if skip:
+                gHp.copy_(gH)
+            _linear_bwd(_rows(gM, 32), 32, _rows(Hprev, 32), 32, B * n, W=g.Ws[l], w_layout=1, Gin=_rows(gHp, 32), accumulate=skip,
+                        dW=G(g.Ws[l]), dev=dev)
+        else:
+            _linear_bwd(_rows(gH, 32), 32, _rows(sv['M'][l], 32), 32, B * n, W=g.Ws[l], w_layout=1, mask=_rows(sv['Rl'][l], 32),
+                        Gin=_rows(gM, 32), dW=G(g.Ws[l]), dev=dev)
+            _attn_bwd(sv['A'], Hprev, gM, gH, skip, gHp, gA, l != L - 1, B, n, dev)
         gH = gHp
     gX = gH                                         # gradient w.r.t. X from the layer stack
     rc = lib.rgl_sim_bwd(_lib.ptr(sv['A']), _lib.ptr(gA), _lib.ptr(sv['X']), _lib.ptr(sv['Y']), _lib.ptr(gY), _lib.ptr(gX),
@@ -104,12 +146,12 @@ def _graph_backward(g, sv, robot, humans, gH, G, dev):
     _linear_bwd(_rows(gY, 32), 32, _rows(sv['X'], 32), 32, B * n, W=g.w_a, w_layout=1, Gin=_rows(gX, 32), accumulate=True,
                 dW=G(g.w_a), dev=dev)
     # embeddings: robot rows (node 0) and human rows (nodes 1..Nh) of gX, addressed in place as grouped rows
-    _linear_bwd(_rows(gX, 32, 1, n * 32), 32, _rows(sv['a1r'], 64), 64, B, W=g.w_r[2].weight, mask=_rows(sv['X'], 32, 1, n * 32),
+    _linear_bwd(_rows(gX, 32, 1, n * 32), 32, sv['a1r'], 64, B, W=g.w_r[2].weight, mask=_rows(sv['X'], 32, 1, n * 32),
                 Gin=_rows(ga_r, 64), dW=G(g.w_r[2].weight), db=G(g.w_r[2].bias), dev=dev)
-    _linear_bwd(_rows(ga_r, 64), 64, _rows(robot, 9), 9, B, mask=_rows(sv['a1r'], 64), dW=G(g.w_r[0].weight), db=G(g.w_r[0].bias), dev=dev)
-    _linear_bwd(_rows(gX, 32, Nh, n * 32, offset=32), 32, _rows(sv['a1h'], 64), 64, B * Nh, W=g.w_h[2].weight,
+    _linear_bwd(_rows(ga_r, 64), 64, _rows(robot, 9), 9, B, mask=sv['a1r'], dW=G(g.w_r[0].weight), db=G(g.w_r[0].bias), dev=dev)
+    _linear_bwd(_rows(gX, 32, Nh, n * 32, offset=32), 32, sv['a1h'], 64, B * Nh, W=g.w_h[2].weight,
                 mask=_rows(sv['X'], 32, Nh, n * 32, offset=32), Gin=_rows(ga_h, 64), dW=G(g.w_h[2].weight), db=G(g.w_h[2].bias), dev=dev)
-    _linear_bwd(_rows(ga_h, 64), 64, _rows(humans, 5), 5, B * Nh, mask=_rows(sv['a1h'], 64), dW=G(g.w_h[0].weight),
+    _linear_bwd(_rows(ga_h, 64), 64, _rows(humans, 5), 5, B * Nh, mask=sv['a1h'], dW=G(g.w_h[0].weight),
                 db=G(g.w_h[0].bias), dev=dev)
 
 
@@ -207,10 +249,10 @@ class _StatePredTrain(torch.autograd.Function):
             gmh = _carve([B * Nh * 64], dev)[0].view(B * Nh, 64)
             gH = gHflat.view(B, n, 32)                    # gradient w.r.t. H_L: human rows only (the head drops node 0)
             HL = sv['Hl'][L - 1]
-            _linear_bwd(_rows(gS, 5), 5, _rows(sv['mh'], 64), 64, B * Nh, W=mp[2].weight, Gin=_rows(gmh, 64), dW=G(mp[2].weight),
+            _linear_bwd(_rows(gS, 5), 5, sv['mh'], 64, B * Nh, W=mp[2].weight, Gin=_rows(gmh, 64), dW=G(mp[2].weight),
                         db=G(mp[2].bias), dev=dev)
             _linear_bwd(_rows(gmh, 64), 64, _rows(HL, 32, Nh, n * 32, offset=32), 32, B * Nh, W=None if detach else mp[0].weight,
-                        mask=_rows(sv['mh'], 64), Gin=None if detach else _rows(gH, 32, Nh, n * 32, offset=32),
+                        mask=sv['mh'], Gin=None if detach else _rows(gH, 32, Nh, n * 32, offset=32),
                         dW=G(mp[0].weight), db=G(mp[0].bias), dev=dev)
             if not detach:
                 _graph_backward(g, sv, robot, humans, gH, G, dev)
