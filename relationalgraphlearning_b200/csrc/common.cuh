@@ -65,7 +65,9 @@ constexpr int T_W1   = T_W0 + 2048;             // emb layer 2, stacked along n:
 constexpr int T_WA   = T_W1 + 8192;             // layer-0 tile, stacked along n: rows 0-31 = w_a^T, rows 32-63 = Ws[0]^T (one N=64 MMA gives
                                                 //   Y = X w_a and X Ws[0] from a single A operand): hi [64][32], lo at +2048
 constexpr int T_WS1  = T_WA + 4096;             // layers l >= 1: Ws[l]^T hi [32][32] at T_WS1 + (l-1)*2048, lo at +1024
-__host__ __device__ constexpr int tc_bias_off(int L) { return T_WS1 + (L - 1) * 2048; }   // [0,32) = w_h.2.bias, [32,64) = w_r.2.bias
+__host__ __device__ constexpr int tc_bias_off(int L) { return T_WS1 + (L - 1) * 2048; }   // [0,32) = w_h.2.bias, [TC_RBIAS, +32) = w_r.2.bias
+constexpr int TC_RBIAS = 36;                    // robot bias 144 B after the human bias (4 banks apart: a quarter-warp that holds robot
+                                                // AND human rows reads both without a bank conflict; at +32 floats the two alias)
 __host__ __device__ constexpr int tc_graph_floats(int L) { return tc_bias_off(L) + 256; }
 __host__ __device__ constexpr int graph_tc_off(int L) { return (graph_floats(L) + 63) & ~63; }     // 256 B aligned
 __host__ __device__ constexpr int graph_floats_total(int L) { return graph_tc_off(L) + tc_graph_floats(L); }

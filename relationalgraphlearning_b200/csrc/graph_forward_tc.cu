@@ -55,6 +55,9 @@ void tc_trace_reset() { unsigned long long z[32] = {}; cudaMemcpyToSymbol(g_tc_t
 #define TC_MARK(k) do { } while (0)
 #endif
 
+// state -> row of the humans tensor (humans_bcast consecutive states share one human set); the common hb == 1 skips a 64-bit division
+__device__ __forceinline__ long hgroup(long gs, int hb) { return hb == 1 ? gs : (long)((unsigned long long)gs / (unsigned)hb); }
+
 // --------------------------------------------------------------------------------------------------- kernel
 constexpr int TC_COLS = 128;          // TMEM columns per group: [0,64) accumulators, [64,96) A hi, [96,128) A lo
 constexpr int C_D = 0, C_AHI = 64, C_ALO = 96;
@@ -103,7 +106,7 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tc_kern
 #pragma unroll
                 for (int k = 0; k < RD; ++k) xr[k] = __ldg(p + k);
             } else {
-                const float* p = a.humans + ((gs / a.hb) * Nh + hum) * HD;
+                const float* p = a.humans + (hgroup(gs, a.hb) * Nh + hum) * HD;
 #pragma unroll
                 for (int k = 0; k < HD; ++k) xr[k] = __ldg(p + k);
             }
@@ -114,7 +117,7 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tc_kern
     auto prefetch_raw = [&](int tile) {
         const long gs = (long)tile * SPT + s_loc;
         if (tile < ntiles && row_used && gs < a.B) {
-            const float* p = is_robot ? a.robot + gs * RD : a.humans + ((gs / a.hb) * Nh + hum) * HD;
+            const float* p = is_robot ? a.robot + gs * RD : a.humans + (hgroup(gs, a.hb) * Nh + hum) * HD;
             asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
             asm volatile("prefetch.global.L2 [%0];" :: "l"(p + (is_robot ? RD - 1 : HD - 1)));
         }
@@ -240,7 +243,7 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tc_kern
             mma_wait();
             TC_MARK(5);   // after: mma_wait()
             tmem_ld64(tl + C_D, h0, h1);     // h0 = human-weight version, h1 = robot-weight version
-            const float* bias = tw + tc_bias_off(a.L) + (is_robot ? 32 : 0);
+            const float* bias = tw + tc_bias_off(a.L) + (is_robot ? TC_RBIAS : 0);
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const float4 b = lds128(bias + 4 * c);

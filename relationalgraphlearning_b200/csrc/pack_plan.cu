@@ -57,7 +57,8 @@ __device__ void pack_graph_tc(const RglGraphParams& p, float* tc, int t, int nt)
         for (int l = 1; l < p.num_layer; ++l) tc_put(tc + T_WS1 + (l - 1) * 2048, 1024, nn, k, p.Ws[l][k * XD + nn]);
     }
     float* b = tc + tc_bias_off(p.num_layer);
-    for (int idx = t; idx < 256; idx += nt) b[idx] = idx < XD ? p.wh1_b[idx] : idx < 2 * XD ? p.wr1_b[idx - XD] : 0.f;
+    for (int idx = t; idx < 256; idx += nt)
+        b[idx] = idx < XD ? p.wh1_b[idx] : (idx >= TC_RBIAS && idx < TC_RBIAS + XD) ? p.wr1_b[idx - TC_RBIAS] : 0.f;
 }
 
 __global__ void pack_graph_kernel(RglGraphParams p, float* out) {
