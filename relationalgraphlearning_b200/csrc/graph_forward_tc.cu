@@ -135,6 +135,7 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tc_kern
     // PDL: everything above (TMEM allocation, barrier set-up) may overlap the tail of the previous kernel on the stream;
     // the states, the packed weights and every output buffer are only touched after this point
     pdl_wait();
+    if (a.flags & RGL_INTERNAL_PDL_EARLY) pdl_trigger();      // small grids: let the next kernel's CTAs launch right away (kernels.h)
     load_raw(tile);                          // the first tile's raw rows: in flight under the weight TMA
     if (tid == 0) {
         // stage 0: layer-1 embedding tiles (the first MMA needs only these); stage 1: everything else
@@ -493,6 +494,7 @@ static cudaError_t launch_tc(const GraphArgs& a, int num_sms, size_t max_smem, c
     const size_t smem = tc_smem_bytes(a.L, a.mw != nullptr, G);
     if (smem > max_smem) return cudaErrorInvalidConfiguration;
     GraphArgs b = a;
+    if (pdl_early(a.B)) b.flags |= RGL_INTERNAL_PDL_EARLY;
     const int spt = 128 / n;
     b.ntiles = (a.B + spt - 1) / spt;
     if (cudaError_t e = ensure_dyn_smem(graph_forward_tc_kernel<N, G>, (int)max_smem)) return e;

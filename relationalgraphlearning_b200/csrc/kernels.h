@@ -45,6 +45,16 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
+// Internal flag bit of GraphArgs::flags (never part of the C ABI): trigger the programmatic launch of the next kernel at the START
+// of this one instead of at its output phase.  Policy (pdl_early): RGL_PDL_EARLY=1 forces it, =0 forbids it.
+#define RGL_INTERNAL_PDL_EARLY (1 << 30)
+static inline bool pdl_early(int B) {
+    static const char* env = getenv("RGL_PDL_EARLY");
+    if (env) return env[0] == '1';
+    (void)B;
+    return false;
+}
+
 typedef RglGraphSave GraphSave;      // optional activation saves of the training forward (include/rgl_b200.h)
 
 struct GraphArgs {
