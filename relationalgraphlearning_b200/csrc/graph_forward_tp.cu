@@ -78,7 +78,8 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tp_kern
     float* tw = smem;                               // graph operand tiles (1024 B aligned)
     float* tm = tw + twf;                           // motion operand tiles (only when S is requested)
     float* xf_all = tm + (a.mw ? TMOTION_FLOATS : 0);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(xf_all + G * (XF_GROUP / 4));      // [0],[1] weights; [2+g] group g
+    float* stage_all = xf_all + G * (XF_GROUP / 4);                                 // SAVE only: 4 KB per warp (coalesced activation saves)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stage_all + (SAVE ? G * 4096 : 0));  // [0],[1] weights; [2+g] group g
     uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 2 + G);
 
     const int tid = threadIdx.x, gt = tid & 127;
@@ -168,6 +169,33 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tp_kern
     auto publish = [&]() { TC_MARK(20); tmem_st_wait(); TC_MARK(23); tc_fence_before(); group_sync(); };
 
     const uint32_t my_row = row_ptr(xf_s, gt);
+    // ---- training saves (SAVE): a warp's valid rows are CONSECUTIVE rows of the [B*n, .] activation tensors (state-major tiles),
+    // so each warp transposes its rows through 4 KB of shared memory and writes them with fully coalesced 512-byte stores
+    // (a thread writing its own 128-byte row costs 32 partial-sector requests per instruction: 2.4 TB/s instead of HBM speed)
+    const uint32_t stage_s = SAVE ? __shfl_sync(0xffffffffu, smem_u32(stage_all), 0) + (uint32_t)(grp * 4 + wq) * 4096u : 0u;
+    const int lane = tid & 31;
+    auto warp_save = [&](float* base, int pitch, long grow_, bool ok, const float (&v)[32]) {
+        // base: tensor base (+ column offset); pitch: floats per tensor row; grow_: this lane's tensor row; ok: the lane holds a real row
+        const unsigned okm = __ballot_sync(0xffffffffu, ok);
+        if (okm == 0u) return;
+        const int di = __popc(okm & ((1u << lane) - 1u));                 // dense index of this lane's row inside the warp's block
+        const int nrow = __popc(okm);
+        const long first = __shfl_sync(0xffffffffu, grow_, __ffs(okm) - 1);  // tensor row of the block's first row
+        __syncwarp();                                                      // the previous save has been copied out
+        if (ok) {
+            const uint32_t rp = stage_s + di * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                sts128s(rp + (((c ^ di) & 7) << 4), make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int q = k * 32 + lane, r = q >> 3, c = q & 7;
+            if (r < nrow)
+                *reinterpret_cast<float4*>(base + (first + r) * pitch + 4 * c) = lds128s(stage_s + r * 128 + (((c ^ r) & 7) << 4));
+        }
+    };
     bool first = true;
 
     for (; tile < ntiles; tile += tstride) {
@@ -216,7 +244,7 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tp_kern
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(__uint_as_float(h0[j]), 0.f);
-            if (saving) save_row32(a.sv.a1r + grow * 64, v);            // relu(hidden) [B, n, 64], columns 0-31
+            if (SAVE) warp_save(a.sv.a1r, 64, grow, saving, v);            // relu(hidden) [B, n, 64], columns 0-31
             st_split<32>(tl + C_AHI, tl + C_ALO, v);
             publish();
             TC_MARK(2);   // after: publish()
@@ -231,7 +259,7 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tp_kern
             }
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(__uint_as_float(h1[j]), 0.f);
-            if (saving) save_row32(a.sv.a1r + grow * 64 + 32, v);       // columns 32-63
+            if (SAVE) warp_save(a.sv.a1r + 32, 64, grow, saving, v);       // columns 32-63
             mma_wait();                      // first half consumed: its A columns may be overwritten
             TC_MARK(3);   // after: mma_wait()
             st_split<32>(tl + C_AHI, tl + C_ALO, v);
@@ -260,7 +288,7 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tp_kern
             }
         }
         xf_store_row(my_row, x);             // feature rows for the neighbours' similarity logits
-        if (saving) save_row32(a.sv.X + grow * 32, x);
+        if (SAVE) warp_save(a.sv.X, 32, grow, saving, x);
 
         // ================= GCN layers: H' = relu(A (H W_l)) (+ H) =================
         // (the reference evaluates (A H) W_l; the products are reassociated so that H W_l shares its A operand with Y = H w_a)
@@ -301,11 +329,11 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tp_kern
                 {
                     uint32_t yr[32];
                     tmem_ld32(tl + C_D, yr);
-                    if (saving && l == 0) {
+                    if (SAVE && l == 0) {
+                        float yv[32];
 #pragma unroll
-                        for (int c = 0; c < 8; ++c)
-                            *reinterpret_cast<float4*>(a.sv.Y + grow * 32 + 4 * c) = make_float4(__uint_as_float(yr[4 * c]), __uint_as_float(yr[4 * c + 1]),
-                                                                                                   __uint_as_float(yr[4 * c + 2]), __uint_as_float(yr[4 * c + 3]));
+                        for (int c = 0; c < 32; ++c) yv[c] = __uint_as_float(yr[c]);
+                        warp_save(a.sv.Y, 32, grow, saving, yv);
                     }
                     // own row's Y at my half / partner row's Y at my half (the partner sends the half it does not use itself)
                     f32x2 ya[8], yb[8];
@@ -364,11 +392,14 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tp_kern
                 uint32_t hw[32];
                 tmem_ld32(tl + C_D + 32, hw);
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const float4 v4 = make_float4(__uint_as_float(hw[4 * c]), __uint_as_float(hw[4 * c + 1]), __uint_as_float(hw[4 * c + 2]),
-                                                  __uint_as_float(hw[4 * c + 3]));
-                    sts128s(my_row + c * 16, v4);
-                    if (saving) *reinterpret_cast<float4*>(a.sv.M[l] + grow * 32 + 4 * c) = v4;      // Z_l = H_{l-1} W_l (reassociated layer)
+                for (int c = 0; c < 8; ++c)
+                    sts128s(my_row + c * 16, make_float4(__uint_as_float(hw[4 * c]), __uint_as_float(hw[4 * c + 1]),
+                                                           __uint_as_float(hw[4 * c + 2]), __uint_as_float(hw[4 * c + 3])));
+                if (SAVE) {                                   // Z_l = H_{l-1} W_l (reassociated layer)
+                    float zv[32];
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) zv[c] = __uint_as_float(hw[c]);
+                    warp_save(a.sv.M[l], 32, grow, saving, zv);
                 }
             }
             tc_fence_before();
@@ -377,6 +408,7 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tp_kern
             // value path, last layer: only node 0 is consumed -- the pair (node 0, node 1) computes that one row
             const bool pair_active = !robot_only || node < 2;
             const unsigned pmask = __ballot_sync(0xffffffffu, pair_active);          // both lanes of a pair are in or out together
+            float rl[SAVE ? 32 : 1];
             if (pair_active) {
                 f32x2 acc_a[8], acc_b[8];                    // my 16 columns of the own row / of the partner's row
 #pragma unroll
@@ -405,9 +437,9 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tp_kern
                     const float r0_ = __shfl_xor_sync(pmask, s0_, 1), r1_ = __shfl_xor_sync(pmask, s1_, 1);
                     const float lo0 = odd ? r0_ : m0, lo1 = odd ? r1_ : m1;       // columns 2c, 2c+1
                     const float hi0 = odd ? m0 : r0_, hi1 = odd ? m1 : r1_;       // columns 16+2c, 17+2c
-                    if (saving) {            // relu(A Z_l) before the skip add (the relu mask of the backward)
-                        *reinterpret_cast<float2*>(a.sv.Rl[l] + grow * 32 + 2 * c) = make_float2(fmaxf(lo0, 0.f), fmaxf(lo1, 0.f));
-                        *reinterpret_cast<float2*>(a.sv.Rl[l] + grow * 32 + 16 + 2 * c) = make_float2(fmaxf(hi0, 0.f), fmaxf(hi1, 0.f));
+                    if (SAVE) {              // relu(A Z_l) before the skip add (the relu mask of the backward)
+                        rl[2 * c] = fmaxf(lo0, 0.f); rl[2 * c + 1] = fmaxf(lo1, 0.f);
+                        rl[16 + 2 * c] = fmaxf(hi0, 0.f); rl[17 + 2 * c] = fmaxf(hi1, 0.f);
                     }
                     if (skip) {
                         x[2 * c] += fmaxf(lo0, 0.f); x[2 * c + 1] += fmaxf(lo1, 0.f);
@@ -418,7 +450,10 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tp_kern
                     }
                 }
             }
-            if (saving) save_row32(a.sv.Hl[l] + grow * 32, x);
+            if (SAVE) {
+                warp_save(a.sv.Rl[l], 32, grow, saving, reinterpret_cast<const float(&)[32]>(rl));
+                warp_save(a.sv.Hl[l], 32, grow, saving, x);
+            }
             if (!last && layerwise) {                        // the next layer's similarity needs the new feature rows
                 group_sync();
                 TC_MARK(10);   // after: group_sync()
@@ -531,13 +566,13 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tp_kern
 }
 
 // ---------------------------------------------------------------------------------------------------
-static size_t tp_smem_bytes(int L, bool motion, int G) {
-    return 1024 + ((size_t)tc_graph_floats(L) + (motion ? TMOTION_FLOATS : 0) + (size_t)G * (XF_GROUP / 4)) * 4 + (2 + G) * 8 + 16;
+static size_t tp_smem_bytes(int L, bool motion, int G, bool save) {
+    return 1024 + ((size_t)tc_graph_floats(L) + (motion ? TMOTION_FLOATS : 0) + (size_t)G * (XF_GROUP / 4) + (save ? (size_t)G * 4096 : 0)) * 4 + (2 + G) * 8 + 16;
 }
 
 template <int N, int G, bool SAVE>
 static cudaError_t launch_tp(const GraphArgs& a, int num_sms, size_t max_smem, cudaStream_t st) {
-    const size_t smem = tp_smem_bytes(a.L, a.mw != nullptr, G);
+    const size_t smem = tp_smem_bytes(a.L, a.mw != nullptr, G, SAVE);
     if (smem > max_smem) return cudaErrorInvalidConfiguration;
     GraphArgs b = a;
     if (pdl_early(a.B)) b.flags |= RGL_INTERNAL_PDL_EARLY;
