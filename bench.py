@@ -837,7 +837,8 @@ def main():
                          'peak_source': 'measured fp32-FMA peak of this pool (tools/fma_peak.cu); the shared-weight GEMMs (90 %% of the MACs) run '
                                         'on tcgen05 as 3xTF32, so the fraction can exceed 1 (measured bf16 tensor peak: %s TFLOP/s)' % peaks.get('bf16_tflops'),
                          'traffic': traffic, 'traffic_note': traffic_note,
-                         'kernel': 'graph_forward_tc_kernel' if args.workload == 'graph' else 'graph_forward_tc_kernel (+ value_head_tc_kernel)',
+                         'kernel': {'graph': 'graph_forward_tp_kernel<6,2>', 'value': 'graph_forward_tc_kernel (+ value_head_tc_kernel)',
+                                    'statepred': 'graph_forward_tp_kernel'}[args.workload] if nh == 5 else 'graph_forward_tp/tc_kernel',
                          'launch_us': kernel_ms * 1e3,
                          'launch_timing': 'CUDA events around %d back-to-back launches on one stream (graph replay over the whole > L2 input pool)' % (5 * KG),
                          'algorithmic_bytes_per_state': abytes, 'algorithmic_flops_per_state': aflops,

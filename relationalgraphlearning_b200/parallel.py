@@ -217,6 +217,16 @@ class FlatGrads(object):
             self.comm = None
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    key = (device.type, device.index)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device)
+    return _SIDE_STREAMS[key]
+
+
 def dp_value_step(value_estimator, target_model, optimizer, reducer, robot, humans, rewards, next_robot, next_humans,
                   gamma_bar, global_batch):
     """One data-parallel value-network step on this rank's shard (trainer.py:122-131).  `reducer`: FlatGrads (native
@@ -227,9 +237,21 @@ def dp_value_step(value_estimator, target_model, optimizer, reducer, robot, huma
     Returns the local loss contribution (a tensor; sum over ranks = the global mean loss).
     """
     reducer.step_begin(optimizer)
-    out = value_estimator((robot, humans))
-    with torch.no_grad():
-        v_next = target_model((next_robot, next_humans))
+    if robot.is_cuda:
+        # the target-network forward does not depend on the online forward: it runs on a side stream (a parallel branch of
+        # the CUDA graph when the step is captured) and joins before the loss
+        cur = torch.cuda.current_stream(robot.device)
+        side = _side_stream(robot.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side), torch.no_grad():
+            v_next = target_model((next_robot, next_humans))
+        out = value_estimator((robot, humans))
+        cur.wait_stream(side)
+        v_next.record_stream(cur)
+    else:
+        out = value_estimator((robot, humans))
+        with torch.no_grad():
+            v_next = target_model((next_robot, next_humans))
     if out.is_cuda:
         from . import training
         loss = training.td_loss(out, rewards, v_next, gamma_bar, global_batch)       # one launch: target, loss, dLoss/dV
