@@ -132,3 +132,21 @@ def test_batched_next_robot_state_rule():
     hs = torch.rand(2, 3, 5)
     nh = lin.linear_motion_approximator(hs)
     assert torch.equal(nh[..., 0], hs[..., 0] + hs[..., 2]) and torch.equal(nh[..., 4], hs[..., 4])
+
+
+def test_argument_validation_of_the_round2_entry_points():
+    """Planner select / backup, TD loss, replay and communicator entry points reject bad arguments before any launch."""
+    lib = _lib.lib()
+    assert lib.rgl_plan_select(None, None, 4, 11, 0.97, 2, None, None, None, None, None, None, None) == -1
+    assert lib.rgl_plan_select(None, None, 0, 11, 0.97, 2, None, None, None, None, None, None, None) == 0      # empty: no-op
+    assert lib.rgl_plan_backup(None, None, None, 4, 2, 0.97, 2, None, None, None) == -1
+    assert lib.rgl_plan_expand(None, None, 4, 5, 1, None, 11, 0.25, 7, None, None, None) == -1                  # unknown kinematics / nulls
+    assert lib.rgl_td_loss(None, None, None, 8, 0.97, 0.125, None, None, None) == -1
+    assert lib.rgl_replay_record_floats(5) == 70 and lib.rgl_replay_record_floats(0) == 0 and lib.rgl_replay_record_floats(32) == 0
+    assert lib.rgl_replay_gather(None, None, 4, 5, None, None, None, None, None, None, None) == -1
+    h = ctypes.c_void_p()
+    assert lib.rgl_comm_create(3, 2, 100, ctypes.byref(h)) == -1          # rank outside the world
+    assert lib.rgl_comm_create(0, 64, 100, ctypes.byref(h)) == -1         # world too large
+    assert b'rgl_comm_create' in lib.rgl_comm_last_error_string()
+    assert lib.rgl_comm_handle_bytes() == 64
+    assert lib.rgl_comm_destroy(None) == 0
