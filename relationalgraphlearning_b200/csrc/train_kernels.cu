@@ -482,7 +482,11 @@ static cudaError_t launch_bwd_mma(LinBwdArgs& a, int num_sms, size_t max_smem, c
     if (cudaError_t e = ensure_dyn_smem(rows_linear_bwd_mma_kernel<N8, K16, MROWS, DB>, (int)max_smem)) return e;
     a.ntiles = (a.R + MROWS - 1) / MROWS;
     int per_sm = (int)((227 * 1024) / (sm + 1024));
-    per_sm = per_sm < 1 ? 1 : (per_sm > (DB ? 2 : 1) ? (DB ? 2 : 1) : per_sm);          // matches __launch_bounds__
+    // registers: __launch_bounds__(256, 2) guarantees two CTAs per SM; a third fits when the kernel needs <= 85 registers
+    cudaFuncAttributes fa;
+    int reg_cap = DB ? 2 : 1;
+    if (DB && cudaFuncGetAttributes(&fa, rows_linear_bwd_mma_kernel<N8, K16, MROWS, DB>) == cudaSuccess && fa.numRegs * 256 * 3 <= 65536) reg_cap = 3;
+    per_sm = per_sm < 1 ? 1 : (per_sm > reg_cap ? reg_cap : per_sm);
     const int cap = num_sms * per_sm;
     rows_linear_bwd_mma_kernel<N8, K16, MROWS, DB><<<a.ntiles < cap ? a.ntiles : cap, 256, sm, st>>>(a);
     return cudaGetLastError();
