@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define RGL_B200_VERSION 200          /* major*10000 + minor*100 + patch */
+#define RGL_B200_VERSION 201          /* major*10000 + minor*100 + patch */
 
 #define RGL_X_DIM        32           /* config.gcn.X_dim = final_state_dim (configs/icra_benchmark/config.py:103-108) */
 #define RGL_EMB_HIDDEN   64           /* wr_dims[0] = wh_dims[0] */
@@ -215,9 +215,12 @@ int rgl_linear_bwd(const RglRows* G, int N, const RglRows* mask, const RglRows* 
                    const float* W, int w_layout, const RglRows* Gin, int accumulate,
                    float* dW, float* db, int R, rgl_stream_t stream);
 /* gHprev[b,j,:] = (skip ? gH[b,j,:] : 0) + sum_i A[b,i,j] gM[b,i,:];  gA[b,i,j] (+)= gM[b,i,:] . Hprev[b,j,:]
- * mask (optional, [B,n,32]): gM is multiplied by (mask > 0) on load. */
+ * mask (optional, [B,n,32]): gM is multiplied by (mask > 0) on load.
+ * up_rows in [1,n]: only node rows i < up_rows of gM carry gradient; the others are taken as zero and never read
+ * (1 for the top layer of the value step, whose head reads the robot row only: value_estimator.py:38; n otherwise). */
 int rgl_attn_layer_bwd(const float* A, const float* Hprev, const float* gM, const float* gH, int skip,
-                       float* gHprev, float* gA, int accumulate_gA, int B, int n, const float* mask, rgl_stream_t stream);
+                       float* gHprev, float* gA, int accumulate_gA, int B, int n, const float* mask, int up_rows,
+                       rgl_stream_t stream);
 /* softmax + similarity backward: gY = gS X, gX += gS^T Y with gS = A (gA - rowsum(gA A)) */
 int rgl_sim_bwd(const float* A, const float* gA, const float* X, const float* Y, float* gY, float* gX,
                 int B, int n, rgl_stream_t stream);

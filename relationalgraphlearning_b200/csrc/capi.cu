@@ -267,13 +267,14 @@ int rgl_linear_bwd(const RglRows* G, int N, const RglRows* mask, const RglRows* 
 }
 
 int rgl_attn_layer_bwd(const float* A, const float* Hprev, const float* gM, const float* gH, int skip, float* gHprev, float* gA,
-                       int accumulate_gA, int B, int n, const float* mask, rgl_stream_t stream) {
+                       int accumulate_gA, int B, int n, const float* mask, int up_rows, rgl_stream_t stream) {
     if (B == 0) return RGL_OK;
     if (!A || !Hprev || !gM || !gHprev || !gA || (skip && !gH) || B < 0 || n < 1 || n > 32)
         return fail(RGL_EINVAL, "rgl_attn_layer_bwd: bad argument");
+    if (up_rows < 1 || up_rows > n) return fail(RGL_EINVAL, "rgl_attn_layer_bwd: up_rows must be in [1, n]");
     if (!aligned16(Hprev) || !aligned16(gM) || !aligned16(gHprev) || (gH && !aligned16(gH)) || (mask && !aligned16(mask)))
         return fail(RGL_EALIGN, "rgl_attn_layer_bwd: row buffers must be 16-byte aligned");
-    cudaError_t e = rgl::run_attn_layer_bwd(A, Hprev, gM, gH, skip, gHprev, gA, accumulate_gA, B, n, mask, (cudaStream_t)stream);
+    cudaError_t e = rgl::run_attn_layer_bwd(A, Hprev, gM, gH, skip, gHprev, gA, accumulate_gA, B, n, mask, up_rows, (cudaStream_t)stream);
     return e == cudaSuccess ? RGL_OK : fail_cuda(e, "rgl_attn_layer_bwd");
 }
 

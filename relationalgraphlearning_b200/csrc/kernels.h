@@ -88,7 +88,7 @@ cudaError_t run_linear_bwd(const RglRows* G, int N, const RglRows* mask, const R
                            const RglRows* Gin, int accumulate, float* dW, float* db, int R, int num_sms, size_t max_smem,
                            cudaStream_t st);
 cudaError_t run_attn_layer_bwd(const float* A, const float* Hprev, const float* gM, const float* gH, int skip, float* gHprev,
-                               float* gA, int accumulate_gA, int B, int n, const float* mask, cudaStream_t st);
+                               float* gA, int accumulate_gA, int B, int n, const float* mask, int up_rows, cudaStream_t st);
 cudaError_t run_sim_bwd(const float* A, const float* gA, const float* X, const float* Y, float* gY, float* gX, int B, int n,
                         cudaStream_t st);
 cudaError_t run_gcn_layer(const float* X, const float* A, const float* W, const float* wa, int B, int n, int flags,

@@ -35,6 +35,7 @@ struct LinBwdArgs {
     float* db;            // optional [N]
     int ntiles;
     int vecG, vecX;       // rows of G(+mask) / Xin are 16-byte aligned and N / K are multiples of 4
+    int vecW;             // W is [N][K] with K a multiple of 4 and a 16-byte aligned base: staged with cp.async
 };
 
 constexpr int LT = 64;    // rows per tile
@@ -241,7 +242,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // and spent 95 % of its instructions on index arithmetic (ncu: 2 550 warp instructions per warp and tile for 96 HMMA,
 // instruction-cache hit rate 80 %).
 template <int N8, int K16, int MROWS, bool DB>
-__global__ void __launch_bounds__(256, DB ? 2 : 1) rows_linear_bwd_mma_kernel(const LinBwdArgs a) {
+__global__ void __launch_bounds__(256, (DB || MROWS <= 32) ? 2 : 1) rows_linear_bwd_mma_kernel(const LinBwdArgs a) {
     extern __shared__ __align__(128) float smem[];
     constexpr int NP = N8 * 8, KP = K16 * 16, K8 = K16 * 2;
     constexpr int ldg = ((NP + 31) / 32) * 32 + 8, ldx = ((KP + 31) / 32) * 32 + 8;      // = 8 mod 32 words
@@ -256,7 +257,15 @@ __global__ void __launch_bounds__(256, DB ? 2 : 1) rows_linear_bwd_mma_kernel(co
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
 
-    if (a.W) {
+    if (a.W && a.vecW) {
+        // nn.Linear layout with 16-byte aligned rows: the whole matrix in ONE cp.async group (a single global round trip;
+        // the group is waited for together with the first tile's).  Padding rows / columns are zero-filled.
+        for (int idx = tid; idx < NP * (ldx / 4); idx += 256) {
+            const int nn = idx / (ldx / 4), k = (idx - nn * (ldx / 4)) << 2;
+            const bool in = nn < N && k < K;
+            cp_async16(smem_u32(Ws + nn * ldx + k), in ? a.W + (size_t)nn * K + k : a.W, in ? 16u : 0u);
+        }
+    } else if (a.W) {
         // 8 independent loads in flight per thread (a rolled loop would serialise one global round trip per element)
         for (int base = tid; base < NP * ldx; base += 8 * 256) {
             float v[8];
@@ -484,7 +493,7 @@ static cudaError_t launch_bwd_mma(LinBwdArgs& a, int num_sms, size_t max_smem, c
     int per_sm = (int)((227 * 1024) / (sm + 1024));
     // registers: __launch_bounds__(256, 2) guarantees two CTAs per SM; a third fits when the kernel needs <= 85 registers
     cudaFuncAttributes fa;
-    int reg_cap = DB ? 2 : 1;
+    int reg_cap = (DB || MROWS <= 32) ? 2 : 1;
     if (DB && cudaFuncGetAttributes(&fa, rows_linear_bwd_mma_kernel<N8, K16, MROWS, DB>) == cudaSuccess && fa.numRegs * 256 * 3 <= 65536) reg_cap = 3;
     per_sm = per_sm < 1 ? 1 : (per_sm > reg_cap ? reg_cap : per_sm);
     const int cap = num_sms * per_sm;
@@ -501,6 +510,15 @@ static cudaError_t dispatch_bwd_mma(LinBwdArgs& a, int num_sms, size_t max_smem,
         RGL_BWD_CASE(4, 2, 128, true);
         RGL_BWD_CASE(4, 4, 128, true);
         RGL_BWD_CASE(8, 1, 128, true);
+    }
+    if ((a.R + 63) / 64 <= num_sms) {
+        // fewer 64-row tiles than SMs (the B-row layers: value head, robot embedding): 32-row tiles double the CTAs and the
+        // warps per SM -- these launches are bound by the latency of ONE tile, not by throughput
+        RGL_BWD_CASE(13, 7, 32, false);
+        RGL_BWD_CASE(13, 2, 32, false);
+        RGL_BWD_CASE(1, 7, 32, false);
+        RGL_BWD_CASE(4, 2, 32, true);
+        RGL_BWD_CASE(4, 4, 32, true);
     }
     RGL_BWD_CASE(4, 2, 64, true);       // 32 x 32: GCN layers, w_a, value layer 0          (64-row tiles: two CTAs per SM)
     RGL_BWD_CASE(4, 4, 64, true);       // 32 x 64: embedding layer 2 (w_r.2, w_h.2)
@@ -520,9 +538,11 @@ static cudaError_t dispatch_bwd_mma(LinBwdArgs& a, int num_sms, size_t max_smem,
 //  a quad of lanes splits the row, the dot product is closed with two shuffles)
 // mask (optional, [B,n,32]): gM is multiplied by (mask > 0) on load -- the relu mask of the reassociated layer
 // H' = relu(A (H W)), where this kernel runs FIRST (gM = gH', Hprev = H W) and the linear backward second.
+// up_rows: the first up_rows node rows of gM carry gradient, the others are zero and skipped (1 for the top layer of the
+// value step, whose head reads the robot row only; n otherwise).
 __global__ void attn_layer_bwd_kernel(const float* __restrict__ A, const float* __restrict__ Hprev, const float* __restrict__ gM,
                                       const float* __restrict__ gH, int skip, float* __restrict__ gHprev, float* __restrict__ gA,
-                                      int accumulate_gA, int B, int n, const float* __restrict__ mask) {
+                                      int accumulate_gA, int B, int n, const float* __restrict__ mask, int up_rows) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int q = (int)(t & 3);
     const long long total = (long long)B * n;
@@ -547,8 +567,11 @@ __global__ void attn_layer_bwd_kernel(const float* __restrict__ A, const float* 
     const float* gMb = gM + (size_t)b * n * 32 + 8 * q;
     const float* mkb = mask ? mask + (size_t)b * n * 32 + 8 * q : nullptr;
     float* gAb = gA + (size_t)b * n * n + j;
+    // rows >= up_rows of gM are zero by contract and never read (value head: only the robot row carries gradient)
+    if (!accumulate_gA && q == 0 && live)
+        for (int i = up_rows; i < n; ++i) gAb[i * n] = 0.f;
 #pragma unroll 4
-    for (int i = 0; i < n; ++i) {
+    for (int i = 0; i < up_rows; ++i) {
         const float aij = Ab[i * n];
         const float4 u = *reinterpret_cast<const float4*>(gMb + i * 32), v = *reinterpret_cast<const float4*>(gMb + i * 32 + 4);
         float gm[8] = {u.x, u.y, u.z, u.w, v.x, v.y, v.z, v.w};
@@ -676,6 +699,7 @@ cudaError_t run_linear_bwd(const RglRows* G, int N, const RglRows* mask, const R
     };
     a.vecG = vec_ok(a.G, N) && (a.mask.ptr == nullptr || vec_ok(a.mask, N));
     a.vecX = vec_ok(a.Xin, K);
+    a.vecW = W != nullptr && w_layout == 0 && (K & 3) == 0 && (reinterpret_cast<uintptr_t>(W) & 15u) == 0;
     // N, K <= 64: tensor-core kernel (mma.sync 3xTF32).  RGL_BWD_VARIANT=f keeps the fp32-FMA kernel (experiments only).
     static const char* variant = getenv("RGL_BWD_VARIANT");
     if (!(variant && variant[0] == 'f')) {
@@ -698,9 +722,9 @@ cudaError_t run_linear_bwd(const RglRows* G, int N, const RglRows* mask, const R
 }
 
 cudaError_t run_attn_layer_bwd(const float* A, const float* Hprev, const float* gM, const float* gH, int skip, float* gHprev,
-                               float* gA, int accumulate_gA, int B, int n, const float* mask, cudaStream_t st) {
+                               float* gA, int accumulate_gA, int B, int n, const float* mask, int up_rows, cudaStream_t st) {
     const long long threads = (long long)B * n * 4;
-    attn_layer_bwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(A, Hprev, gM, gH, skip, gHprev, gA, accumulate_gA, B, n, mask);
+    attn_layer_bwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(A, Hprev, gM, gH, skip, gHprev, gA, accumulate_gA, B, n, mask, up_rows);
     return cudaGetLastError();
 }
 

@@ -105,17 +105,18 @@ def _graph_forward_train(g, robot, humans, extra_sizes, motion_blob=None, want_E
     return sv, v[8 + 3 * L:], E, S
 
 
-def _attn_bwd(A, Hprev, gM, gH, skip, gHprev, gA, accumulate_gA, B, n, dev, mask=None):
+def _attn_bwd(A, Hprev, gM, gH, skip, gHprev, gA, accumulate_gA, B, n, dev, mask=None, up_rows=None):
     rc = _lib.lib().rgl_attn_layer_bwd(_lib.ptr(A), _lib.ptr(Hprev), _lib.ptr(gM), _lib.ptr(gH) if gH is not None else None, 1 if skip else 0,
                                        _lib.ptr(gHprev), _lib.ptr(gA), 1 if accumulate_gA else 0, B, n,
-                                       _lib.ptr(mask) if mask is not None else None, _lib.stream_ptr(dev))
+                                       _lib.ptr(mask) if mask is not None else None, n if up_rows is None else up_rows, _lib.stream_ptr(dev))
     _lib.check(rc, 'rgl_attn_layer_bwd')
     ops._count(1)
 
 
-def _graph_backward(g, sv, robot, humans, gH, G, dev):
+def _graph_backward(g, sv, robot, humans, gH, G, dev, top_rows=None):
     """Back-propagate gH = dLoss/dH_L [B,n,32] through the GCN layers, the similarity and the embeddings.
-    G(p) returns the (zero-initialised) gradient buffer of parameter p; gradients are accumulated into them."""
+    G(p) returns the (zero-initialised) gradient buffer of parameter p; gradients are accumulated into them.
+    top_rows: only the first top_rows node rows of gH are non-zero (1 for the value head, which reads the robot row)."""
     B, Nh = robot.size(0), humans.size(1)
     n, L = Nh + 1, g.num_layer
     skip = bool(g.skip_connection)
@@ -128,9 +129,11 @@ def _graph_backward(g, sv, robot, humans, gH, G, dev):
         if sv['tc']:
             # H_l = relu(A Z) (+ H_{l-1}), Z = H_{l-1} W_l:   gZ = A^T (gH . mask),  gA (+)= (gH . mask) Z^T,
             #                                                 dW_l = H_{l-1}^T gZ,    gH_{l-1} = gZ W_l^T (+ gH)
-            _attn_bwd(sv['A'], sv['M'][l], gH, None, False, gM, gA, l != L - 1, B, n, dev, mask=sv['Rl'][l])
+            # (skip connection: gH has been consumed by the attention backward, so gZ W^T is accumulated into it in place)
+            _attn_bwd(sv['A'], sv['M'][l], gH, None, False, gM, gA, l != L - 1, B, n, dev, mask=sv['Rl'][l],
+                      up_rows=top_rows if l == L - 1 else None)
             if skip:
-                gHp.copy_(gH)
+                gHp = gH
             _linear_bwd(_rows(gM, 32), 32, _rows(Hprev, 32), 32, B * n, W=g.Ws[l], w_layout=1, Gin=_rows(gHp, 32), accumulate=skip,
                         dW=G(g.Ws[l]), dev=dev)
         else:
@@ -145,14 +148,30 @@ def _graph_backward(g, sv, robot, humans, gH, G, dev):
     ops._count(1)
     _linear_bwd(_rows(gY, 32), 32, _rows(sv['X'], 32), 32, B * n, W=g.w_a, w_layout=1, Gin=_rows(gX, 32), accumulate=True,
                 dW=G(g.w_a), dev=dev)
-    # embeddings: robot rows (node 0) and human rows (nodes 1..Nh) of gX, addressed in place as grouped rows
-    _linear_bwd(_rows(gX, 32, 1, n * 32), 32, sv['a1r'], 64, B, W=g.w_r[2].weight, mask=_rows(sv['X'], 32, 1, n * 32),
-                Gin=_rows(ga_r, 64), dW=G(g.w_r[2].weight), db=G(g.w_r[2].bias), dev=dev)
-    _linear_bwd(_rows(ga_r, 64), 64, _rows(robot, 9), 9, B, mask=sv['a1r'], dW=G(g.w_r[0].weight), db=G(g.w_r[0].bias), dev=dev)
+    # embeddings: robot rows (node 0) and human rows (nodes 1..Nh) of gX, addressed in place as grouped rows.
+    # The robot branch (B rows: less than one wave of CTAs) runs on a side stream next to the human branch (B*Nh rows);
+    # inside a captured step it becomes a parallel branch of the graph.
+    cur, side = torch.cuda.current_stream(dev), _bwd_side_stream(dev)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        _linear_bwd(_rows(gX, 32, 1, n * 32), 32, sv['a1r'], 64, B, W=g.w_r[2].weight, mask=_rows(sv['X'], 32, 1, n * 32),
+                    Gin=_rows(ga_r, 64), dW=G(g.w_r[2].weight), db=G(g.w_r[2].bias), dev=dev)
+        _linear_bwd(_rows(ga_r, 64), 64, _rows(robot, 9), 9, B, mask=sv['a1r'], dW=G(g.w_r[0].weight), db=G(g.w_r[0].bias), dev=dev)
     _linear_bwd(_rows(gX, 32, Nh, n * 32, offset=32), 32, sv['a1h'], 64, B * Nh, W=g.w_h[2].weight,
                 mask=_rows(sv['X'], 32, Nh, n * 32, offset=32), Gin=_rows(ga_h, 64), dW=G(g.w_h[2].weight), db=G(g.w_h[2].bias), dev=dev)
     _linear_bwd(_rows(ga_h, 64), 64, _rows(humans, 5), 5, B * Nh, mask=sv['a1h'], dW=G(g.w_h[0].weight),
                 db=G(g.w_h[0].bias), dev=dev)
+    cur.wait_stream(side)           # every buffer the side branch touched outlives this join
+
+
+_BWD_SIDE = {}
+
+
+def _bwd_side_stream(dev):
+    key = (dev.type, dev.index)
+    if key not in _BWD_SIDE:
+        _BWD_SIDE[key] = torch.cuda.Stream(dev)
+    return _BWD_SIDE[key]
 
 
 def _grad_buffers(plist, extra, dev, sink=None):
@@ -214,7 +233,7 @@ class _ValueTrain(torch.autograd.Function):
                         dW=G(vn[2].weight), db=G(vn[2].bias), dev=dev)
             _linear_bwd(_rows(g0, 32), 32, _rows(E, 32), 32, B, W=vn[0].weight, mask=_rows(v0, 32),
                         Gin=_rows(gH, 32, 1, n * 32), dW=G(vn[0].weight), db=G(vn[0].bias), dev=dev)
-            _graph_backward(g, sv, robot, humans, gH, G, dev)
+            _graph_backward(g, sv, robot, humans, gH, G, dev, top_rows=1)
         grads = [None if direct else gp[id(p)] for p in ve._train_params()]
         ctx.sv = ctx.acts = None
         return (None, None, None) + tuple(grads)
