@@ -247,7 +247,12 @@ int rgl_value_head_train(const float* E, int B, const float* value_packed, float
     if (!aligned16(value_packed)) return fail(RGL_EALIGN, "rgl_value_head_train: packed weights must be 16-byte aligned");
     DevInfo d;
     if (int rc = dev_info(&d)) return rc;
-    cudaError_t e = rgl::run_value_head(E, B, value_packed, V, v0, v1, v2, aligned16(E) ? 1 : 0, d.sms, (cudaStream_t)stream);
+    // same kernel as inference (tcgen05, 3xTF32) with the activation saves written from the epilogues; the fp32-FMA kernel
+    // keeps unaligned buffers and RGL_VALUE_VARIANT=f (experiments only)
+    static const char* variant = getenv("RGL_VALUE_VARIANT");
+    const bool tc = aligned16(E) && aligned16(v0) && aligned16(v1) && aligned16(v2) && !(variant && variant[0] == 'f');
+    cudaError_t e = tc ? rgl::run_value_head_tc_train(E, B, value_packed, V, v0, v1, v2, d.sms, d.max_smem, (cudaStream_t)stream)
+                       : rgl::run_value_head(E, B, value_packed, V, v0, v1, v2, aligned16(E) ? 1 : 0, d.sms, (cudaStream_t)stream);
     return e == cudaSuccess ? RGL_OK : fail_cuda(e, "rgl_value_head_train");
 }
 

@@ -84,6 +84,8 @@ cudaError_t run_value_head(const float* E, int B, const float* vw, float* V, flo
                            cudaStream_t st);
 // tcgen05 value network (value_head_tc.cu): inference only
 cudaError_t run_value_head_tc(const float* E, int B, const float* vw, float* V, int num_sms, size_t max_smem, cudaStream_t st);
+cudaError_t run_value_head_tc_train(const float* E, int B, const float* vw, float* V, float* v0, float* v1, float* v2, int num_sms,
+                                    size_t max_smem, cudaStream_t st);
 cudaError_t run_linear_bwd(const RglRows* G, int N, const RglRows* mask, const RglRows* Xin, int K, const float* W, int w_layout,
                            const RglRows* Gin, int accumulate, float* dW, float* db, int R, int num_sms, size_t max_smem,
                            cudaStream_t st);

@@ -21,9 +21,12 @@ namespace rgl {
 constexpr int VT_COLS = 256;
 constexpr int VC_D = 0, VC_A0 = 128, VC_A1 = 192;      // A buffers: hi at +0, lo at +32
 
-template <int G>
+// SAVE: the training forward -- additionally writes the post-relu activations the backward reads
+// (sv0 [B,32], sv1 / sv2 [B,128] with 100 valid columns; one thread = one row, 16-byte stores).
+template <int G, bool SAVE>
 __global__ void __launch_bounds__(128 * G, 1) value_head_tc_kernel(const float* __restrict__ E, int B, const float* __restrict__ vw,
-                                                                    float* __restrict__ V, int ntiles) {
+                                                                    float* __restrict__ V, int ntiles, float* __restrict__ sv0,
+                                                                    float* __restrict__ sv1, float* __restrict__ sv2) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     float* tw = reinterpret_cast<float*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     uint64_t* bars = reinterpret_cast<uint64_t*>(tw + TVALUE_FLOATS);      // [0..2] weight stages, [3+2g], [4+2g] group g
@@ -110,6 +113,11 @@ __global__ void __launch_bounds__(128 * G, 1) value_head_tc_kernel(const float* 
                 h[4 * c + 2] = fmaxf(__uint_as_float(d[4 * c + 2]) + b.z, 0.f); h[4 * c + 3] = fmaxf(__uint_as_float(d[4 * c + 3]) + b.w, 0.f);
             }
             st_split<32>(tl + VC_A1, tl + VC_A1 + 32, h);
+            if (SAVE && valid) {
+                float4* o = reinterpret_cast<float4*>(sv0 + s * 32);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) o[c] = make_float4(h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]);
+            }
         }
         publish();
         if (issuer) {
@@ -145,6 +153,11 @@ __global__ void __launch_bounds__(128 * G, 1) value_head_tc_kernel(const float* 
                 h1[96 + 4 * c] = fmaxf(__uint_as_float(d8[4 * c]) + b.x, 0.f); h1[96 + 4 * c + 1] = fmaxf(__uint_as_float(d8[4 * c + 1]) + b.y, 0.f);
                 h1[96 + 4 * c + 2] = fmaxf(__uint_as_float(d8[4 * c + 2]) + b.z, 0.f); h1[96 + 4 * c + 3] = fmaxf(__uint_as_float(d8[4 * c + 3]) + b.w, 0.f);
             }
+        }
+        if (SAVE && valid) {
+            float4* o = reinterpret_cast<float4*>(sv1 + s * 128);
+#pragma unroll
+            for (int c = 0; c < 26; ++c) o[c] = make_float4(h1[4 * c], h1[4 * c + 1], h1[4 * c + 2], h1[4 * c + 3]);
         }
         const uint32_t w2 = tw_s + TV_W2 * 4;
         // atom 0 -> A0 (free: layer 0 is done), atom 1 -> A1 (free: layer 1 is done), atom 2 -> A0 after atom 0's MMAs,
@@ -190,8 +203,10 @@ __global__ void __launch_bounds__(128 * G, 1) value_head_tc_kernel(const float* 
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const float4 b = lds128(bias + 160 + 32 * q + 4 * c), w = lds128(bias + 288 + 32 * q + 4 * c);
-                v0 = fmaf(fmaxf(__uint_as_float(d[4 * c]) + b.x, 0.f), w.x, v0); v1 = fmaf(fmaxf(__uint_as_float(d[4 * c + 1]) + b.y, 0.f), w.y, v1);
-                v2 = fmaf(fmaxf(__uint_as_float(d[4 * c + 2]) + b.z, 0.f), w.z, v2); v3 = fmaf(fmaxf(__uint_as_float(d[4 * c + 3]) + b.w, 0.f), w.w, v3);
+                const float4 r = make_float4(fmaxf(__uint_as_float(d[4 * c]) + b.x, 0.f), fmaxf(__uint_as_float(d[4 * c + 1]) + b.y, 0.f),
+                                             fmaxf(__uint_as_float(d[4 * c + 2]) + b.z, 0.f), fmaxf(__uint_as_float(d[4 * c + 3]) + b.w, 0.f));
+                v0 = fmaf(r.x, w.x, v0); v1 = fmaf(r.y, w.y, v1); v2 = fmaf(r.z, w.z, v2); v3 = fmaf(r.w, w.w, v3);
+                if (SAVE && valid) reinterpret_cast<float4*>(sv2 + s * 128)[8 * q + c] = r;
             }
         }
         {
@@ -200,8 +215,10 @@ __global__ void __launch_bounds__(128 * G, 1) value_head_tc_kernel(const float* 
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 const float4 b = lds128(bias + 160 + 96 + 4 * c), w = lds128(bias + 288 + 96 + 4 * c);
-                v0 = fmaf(fmaxf(__uint_as_float(d8[4 * c]) + b.x, 0.f), w.x, v0); v1 = fmaf(fmaxf(__uint_as_float(d8[4 * c + 1]) + b.y, 0.f), w.y, v1);
-                v2 = fmaf(fmaxf(__uint_as_float(d8[4 * c + 2]) + b.z, 0.f), w.z, v2); v3 = fmaf(fmaxf(__uint_as_float(d8[4 * c + 3]) + b.w, 0.f), w.w, v3);
+                const float4 r = make_float4(fmaxf(__uint_as_float(d8[4 * c]) + b.x, 0.f), fmaxf(__uint_as_float(d8[4 * c + 1]) + b.y, 0.f),
+                                             fmaxf(__uint_as_float(d8[4 * c + 2]) + b.z, 0.f), fmaxf(__uint_as_float(d8[4 * c + 3]) + b.w, 0.f));
+                v0 = fmaf(r.x, w.x, v0); v1 = fmaf(r.y, w.y, v1); v2 = fmaf(r.z, w.z, v2); v3 = fmaf(r.w, w.w, v3);
+                if (SAVE && valid) reinterpret_cast<float4*>(sv2 + s * 128)[24 + c] = r;
             }
         }
         if (tile + gridDim.x * G >= ntiles) pdl_trigger();      // last tile of this CTA: the next kernel may start its prologue
@@ -215,22 +232,33 @@ __global__ void __launch_bounds__(128 * G, 1) value_head_tc_kernel(const float* 
     if (warp == 0) tmem_dealloc(tbase, VT_COLS * G);
 }
 
-template <int G>
-static cudaError_t launch_vtc(const float* E, int B, const float* vw, float* V, int num_sms, size_t max_smem, cudaStream_t st) {
+template <int G, bool SAVE>
+static cudaError_t launch_vtc(const float* E, int B, const float* vw, float* V, int num_sms, size_t max_smem, cudaStream_t st,
+                              float* sv0, float* sv1, float* sv2) {
     const size_t smem = 1024 + (size_t)TVALUE_FLOATS * 4 + (3 + 2 * G) * 8 + 16;
     if (smem > max_smem) return cudaErrorInvalidConfiguration;
-    if (cudaError_t e = ensure_dyn_smem(value_head_tc_kernel<G>, (int)max_smem)) return e;
+    if (cudaError_t e = ensure_dyn_smem(value_head_tc_kernel<G, SAVE>, (int)max_smem)) return e;
     const int ntiles = (B + 127) / 128;
     const int want = (ntiles + G - 1) / G;
     const int grid = want < num_sms ? want : num_sms;
-    return launch_pdl(value_head_tc_kernel<G>, dim3(grid), dim3(128 * G), smem, st, E, B, vw, V, ntiles);
+    return launch_pdl(value_head_tc_kernel<G, SAVE>, dim3(grid), dim3(128 * G), smem, st, E, B, vw, V, ntiles, sv0, sv1, sv2);
 }
 
 cudaError_t run_value_head_tc(const float* E, int B, const float* vw, float* V, int num_sms, size_t max_smem, cudaStream_t st) {
     static const char* force = getenv("RGL_TC_VALUE_GROUPS");          // experiments only
     const int ntiles = (B + 127) / 128;
     const int g = force ? atoi(force) : (ntiles > num_sms ? 2 : 1);
-    return g == 2 ? launch_vtc<2>(E, B, vw, V, num_sms, max_smem, st) : launch_vtc<1>(E, B, vw, V, num_sms, max_smem, st);
+    return g == 2 ? launch_vtc<2, false>(E, B, vw, V, num_sms, max_smem, st, nullptr, nullptr, nullptr)
+                  : launch_vtc<1, false>(E, B, vw, V, num_sms, max_smem, st, nullptr, nullptr, nullptr);
+}
+
+// training forward: V plus the activation saves v0 [B,32], v1 / v2 [B,128] (columns >= 100 of v1 / v2: zeros up to 104, the
+// rest untouched -- the backward reads 100)
+cudaError_t run_value_head_tc_train(const float* E, int B, const float* vw, float* V, float* v0, float* v1, float* v2,
+                                    int num_sms, size_t max_smem, cudaStream_t st) {
+    const int ntiles = (B + 127) / 128;
+    return ntiles > num_sms ? launch_vtc<2, true>(E, B, vw, V, num_sms, max_smem, st, v0, v1, v2)
+                            : launch_vtc<1, true>(E, B, vw, V, num_sms, max_smem, st, v0, v1, v2);
 }
 
 }  // namespace rgl

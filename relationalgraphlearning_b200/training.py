@@ -199,10 +199,16 @@ class _ValueTrain(torch.autograd.Function):
         g = ve.graph_model
         robot, humans = ops._check_state(robot, humans)
         B, dev = robot.size(0), robot.device
+        # the value-network weights are (re)packed on a side stream while the graph forward runs
+        cur, side = torch.cuda.current_stream(dev), _bwd_side_stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            vblob = ops.packed_value(ve.value_network, ve._pack_cache, force=ops.capturing())
         sv, ex, E, _ = _graph_forward_train(g, robot, humans, [B, B * 32, B * 128, B * 128], want_E=True)
+        cur.wait_stream(side)
         V, v0, v1, v2 = ex[0].view(B, 1), ex[1].view(B, 32), ex[2].view(B, 128), ex[3].view(B, 128)
         with torch.cuda.device(dev):
-            rc = _lib.lib().rgl_value_head_train(_lib.ptr(E), B, _lib.ptr(ops.packed_value(ve.value_network, ve._pack_cache, force=ops.capturing())),
+            rc = _lib.lib().rgl_value_head_train(_lib.ptr(E), B, _lib.ptr(vblob),
                                                  _lib.ptr(V), _lib.ptr(v0), _lib.ptr(v1), _lib.ptr(v2), _lib.stream_ptr(dev))
         _lib.check(rc, 'rgl_value_head_train')
         ops._count(1)
