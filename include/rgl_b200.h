@@ -221,6 +221,14 @@ int rgl_linear_bwd(const RglRows* G, int N, const RglRows* mask, const RglRows* 
 int rgl_attn_layer_bwd(const float* A, const float* Hprev, const float* gM, const float* gH, int skip,
                        float* gHprev, float* gA, int accumulate_gA, int B, int n, const float* mask, int up_rows,
                        rgl_stream_t stream);
+/* Staged form of the two kernels around it for the RGL_FLAG_TRAIN_TC layer order (a CTA owns whole states and works out
+ * of shared memory; one global round trip instead of n dependent ones):
+ *   gZ[b,j,:] = sum_{i < up_rows} A[b,i,j] (gM[b,i,:] . (mask[b,i,:] > 0));   gA[b,i,j] = gA_in[b,i,j] (if given) + (gM.mask)[b,i,:] . Z[b,j,:]
+ * Without X: gA is written to gA_out.  With X (layer 0): the similarity backward follows in the same kernel, gA never
+ * leaves the chip:  gS = A (gA - rowsum(gA A)),  gY = gS X,  gX (gx_accumulate ? += : =) gS^T Y.   gX may alias gM. */
+int rgl_attn_sim_bwd(const float* A, const float* Z, const float* gM, const float* mask, int up_rows, const float* gA_in,
+                     float* gZ, float* gA_out, const float* X, const float* Y, float* gY, float* gX, int gx_accumulate,
+                     int B, int n, rgl_stream_t stream);
 /* softmax + similarity backward: gY = gS X, gX += gS^T Y with gS = A (gA - rowsum(gA A)) */
 int rgl_sim_bwd(const float* A, const float* gA, const float* X, const float* Y, float* gY, float* gX,
                 int B, int n, rgl_stream_t stream);

@@ -76,6 +76,9 @@ EXPORTS = {
                                       ctypes.c_int, ctypes.c_void_p]),
     'rgl_attn_layer_bwd': (ctypes.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, ctypes.c_int, c_float_p, c_float_p,
                                           ctypes.c_int, ctypes.c_int, ctypes.c_int, c_float_p, ctypes.c_int, ctypes.c_void_p]),
+    'rgl_attn_sim_bwd': (ctypes.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, ctypes.c_int, c_float_p, c_float_p, c_float_p,
+                                        c_float_p, c_float_p, c_float_p, c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_void_p]),
     'rgl_sim_bwd': (ctypes.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, ctypes.c_int, ctypes.c_int,
                                    ctypes.c_void_p]),
     'rgl_plan_expand': (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,

@@ -283,6 +283,23 @@ int rgl_attn_layer_bwd(const float* A, const float* Hprev, const float* gM, cons
     return e == cudaSuccess ? RGL_OK : fail_cuda(e, "rgl_attn_layer_bwd");
 }
 
+int rgl_attn_sim_bwd(const float* A, const float* Z, const float* gM, const float* mask, int up_rows, const float* gA_in,
+                     float* gZ, float* gA_out, const float* X, const float* Y, float* gY, float* gX, int gx_accumulate,
+                     int B, int n, rgl_stream_t stream) {
+    if (B == 0) return RGL_OK;
+    if (!A || !Z || !gM || !gZ || B < 0 || n < 1 || n > 32) return fail(RGL_EINVAL, "rgl_attn_sim_bwd: bad argument");
+    if (up_rows < 1 || up_rows > n) return fail(RGL_EINVAL, "rgl_attn_sim_bwd: up_rows must be in [1, n]");
+    if (X ? (!Y || !gY || !gX) : !gA_out) return fail(RGL_EINVAL, "rgl_attn_sim_bwd: X needs Y, gY, gX; without X gA_out is required");
+    if (!aligned16(Z) || !aligned16(gM) || !aligned16(gZ) || (mask && !aligned16(mask)) ||
+        (X && (!aligned16(X) || !aligned16(Y) || !aligned16(gY) || !aligned16(gX))))
+        return fail(RGL_EALIGN, "rgl_attn_sim_bwd: row buffers must be 16-byte aligned");
+    DevInfo d;
+    if (int rc = dev_info(&d)) return rc;
+    cudaError_t e = rgl::run_attn_sim_bwd(A, Z, gM, mask, up_rows, gA_in, gZ, gA_out, X, Y, gY, gX, gx_accumulate, B, n, d.max_smem,
+                                          (cudaStream_t)stream);
+    return e == cudaSuccess ? RGL_OK : fail_cuda(e, "rgl_attn_sim_bwd");
+}
+
 int rgl_sim_bwd(const float* A, const float* gA, const float* X, const float* Y, float* gY, float* gX, int B, int n,
                 rgl_stream_t stream) {
     if (B == 0) return RGL_OK;

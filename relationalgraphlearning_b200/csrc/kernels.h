@@ -91,6 +91,9 @@ cudaError_t run_linear_bwd(const RglRows* G, int N, const RglRows* mask, const R
                            cudaStream_t st);
 cudaError_t run_attn_layer_bwd(const float* A, const float* Hprev, const float* gM, const float* gH, int skip, float* gHprev,
                                float* gA, int accumulate_gA, int B, int n, const float* mask, int up_rows, cudaStream_t st);
+cudaError_t run_attn_sim_bwd(const float* A, const float* Z, const float* gM, const float* mask, int up_rows, const float* gA_in,
+                             float* gZ, float* gA_out, const float* X, const float* Y, float* gY, float* gX, int gx_accumulate,
+                             int B, int n, size_t max_smem, cudaStream_t st);
 cudaError_t run_sim_bwd(const float* A, const float* gA, const float* X, const float* Y, float* gY, float* gX, int B, int n,
                         cudaStream_t st);
 cudaError_t run_gcn_layer(const float* X, const float* A, const float* W, const float* wa, int B, int n, int flags,

@@ -646,6 +646,163 @@ __global__ void sim_bwd_kernel(const float* __restrict__ A, const float* __restr
     }
 }
 
+// ---- staged layer backward through A, optionally fused with the similarity backward (tcgen05 training forward) ------
+// The two kernels above walk n rows per thread straight from global memory: ncu shows them latency-bound (long-scoreboard
+// stalls 24 of 26 stall cycles per issue, 22 % issue utilisation, 33 / 29 us for 9 / 11 us of traffic at C4).  Here a CTA
+// owns spb whole states, fetches every operand of those states with ONE group of cp.async copies (a single global round
+// trip), and runs the row loops out of shared memory:
+//   part 1   gZ[j] = sum_{i < up_rows} A[i][j] (gM[i] . mask[i]);   gA[i][j] (+)= (gM[i] . mask[i]) . Z[j]
+//   SIM      gS = A (gA - rowsum(gA A));   gY[i] = sum_j gS[i][j] X[j];   gX[j] (+)= sum_i gS[i][j] Y[i]
+// With SIM the attention gradient gA of layer 0 never leaves shared memory.  Thread = (state slot, node, column octet).
+struct AttnSimArgs {
+    const float *A, *Z, *gM, *mask, *gA_in, *X, *Y;
+    float *gZ, *gA_out, *gY, *gX;
+    int up_rows, gx_accumulate, B, n, spb;
+};
+
+__device__ __forceinline__ void cp_async4(uint32_t dst_s, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst_s), "l"(src) : "memory");
+}
+
+template <bool SIM>
+__global__ void __launch_bounds__(256) attn_sim_bwd_kernel(const AttnSimArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    const int n = a.n, nn = n * n, spb = a.spb;
+    const int b0 = blockIdx.x * spb;
+    const int cnt = a.B - b0 < spb ? a.B - b0 : spb;
+    const int tile = spb * n * 32;
+    float* gMs = sm;                              // [spb][n][32] upstream gradient (masked in place)
+    float* Mks = gMs + tile;                      // relu mask
+    float* Zs = Mks + tile;                       // Z_l = H_{l-1} W_l
+    float* Xs = Zs + tile;                        // SIM only
+    float* Ys = Xs + tile;
+    float* As = SIM ? Ys + tile : Xs;             // [spb][n*n]
+    float* gAs = As + spb * nn;
+    float* gSs = gAs + spb * nn;                  // SIM only
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int rows = cnt * n;
+    const size_t g0 = (size_t)b0 * n * 32;
+
+    for (int c = tid; c < rows * 8; c += nt) {
+        const int r = c >> 3, o = r * 32 + ((c & 7) << 2);
+        if (r % n < a.up_rows) {
+            cp_async16(smem_u32(gMs + o), a.gM + g0 + o, 16u);
+            if (a.mask) cp_async16(smem_u32(Mks + o), a.mask + g0 + o, 16u);
+        }
+        cp_async16(smem_u32(Zs + o), a.Z + g0 + o, 16u);
+        if (SIM) {
+            cp_async16(smem_u32(Xs + o), a.X + g0 + o, 16u);
+            cp_async16(smem_u32(Ys + o), a.Y + g0 + o, 16u);
+        }
+    }
+    for (int c = tid; c < cnt * nn; c += nt) {
+        cp_async4(smem_u32(As + c), a.A + (size_t)b0 * nn + c);
+        if (a.gA_in) cp_async4(smem_u32(gAs + c), a.gA_in + (size_t)b0 * nn + c);
+        else gAs[c] = 0.f;
+    }
+    cp_async_commit();
+
+    const int q = tid & 3, r = tid >> 2;
+    const int sl = r / n, j = r - sl * n;
+    const bool live = r < rows;
+    float old[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) old[c] = 0.f;
+    if (SIM && a.gx_accumulate && live) {          // this thread's row of gX, fetched next to the staging copies
+        const float4* p = reinterpret_cast<const float4*>(a.gX + g0 + r * 32 + 8 * q);
+        const float4 u = p[0], v = p[1];
+        old[0] = u.x; old[1] = u.y; old[2] = u.z; old[3] = u.w; old[4] = v.x; old[5] = v.y; old[6] = v.z; old[7] = v.w;
+    }
+    cp_async_wait<0>();
+    if (a.mask) {                                  // in place, by the thread that copied the chunk
+        for (int c = tid; c < rows * 8; c += nt) {
+            const int rr = c >> 3, o = rr * 32 + ((c & 7) << 2);
+            if (rr % n < a.up_rows) {
+                float4 v = lds128(gMs + o);
+                const float4 m = lds128(Mks + o);
+                v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f; v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
+                sts128(gMs + o, v);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- part 1: thread (sl, j, q) ----
+    {
+        float hp[8], acc[8];
+        const int rs = live ? r : 0;               // idle threads shadow row 0 (the shuffles stay warp-wide)
+        const int sls = live ? sl : 0, js = live ? j : 0;
+        const float4 u = lds128(Zs + rs * 32 + 8 * q), v = lds128(Zs + rs * 32 + 8 * q + 4);
+        hp[0] = u.x; hp[1] = u.y; hp[2] = u.z; hp[3] = u.w; hp[4] = v.x; hp[5] = v.y; hp[6] = v.z; hp[7] = v.w;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+        const float* Ab = As + sls * nn + js;
+        float* gAb = gAs + sls * nn + js;
+        const float* gMb = gMs + sls * n * 32 + 8 * q;
+#pragma unroll 2
+        for (int i = 0; i < a.up_rows; ++i) {
+            const float aij = Ab[i * n];
+            const float4 gu = lds128(gMb + i * 32), gv = lds128(gMb + i * 32 + 4);
+            const float gm[8] = {gu.x, gu.y, gu.z, gu.w, gv.x, gv.y, gv.z, gv.w};
+            float d = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) { acc[c] = fmaf(aij, gm[c], acc[c]); d = fmaf(gm[c], hp[c], d); }
+            d += __shfl_xor_sync(0xffffffffu, d, 1);
+            d += __shfl_xor_sync(0xffffffffu, d, 2);
+            if (q == 0 && live) gAb[i * n] += d;
+        }
+        if (live) {
+            float4* o4 = reinterpret_cast<float4*>(a.gZ + g0 + r * 32 + 8 * q);
+            o4[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            o4[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        }
+    }
+    __syncthreads();
+    if (!SIM) {
+        if (a.gA_out)
+            for (int c = tid; c < cnt * nn; c += nt) a.gA_out[(size_t)b0 * nn + c] = gAs[c];
+        return;
+    }
+    // ---- similarity backward: thread (sl, i = j, q) ----
+    if (live) {
+        const int i = j;
+        const float* arow = As + sl * nn + i * n;
+        const float* grow = gAs + sl * nn + i * n;
+        float dot = 0.f;
+        for (int k = 0; k < n; ++k) dot = fmaf(grow[k], arow[k], dot);
+        float acc[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+        const float* Xb = Xs + sl * n * 32 + 8 * q;
+#pragma unroll 2
+        for (int k = 0; k < n; ++k) {
+            const float gs = arow[k] * (grow[k] - dot);
+            if (q == 0) gSs[sl * nn + i * n + k] = gs;
+            const float4 u = lds128(Xb + k * 32), v = lds128(Xb + k * 32 + 4);
+            acc[0] = fmaf(gs, u.x, acc[0]); acc[1] = fmaf(gs, u.y, acc[1]); acc[2] = fmaf(gs, u.z, acc[2]); acc[3] = fmaf(gs, u.w, acc[3]);
+            acc[4] = fmaf(gs, v.x, acc[4]); acc[5] = fmaf(gs, v.y, acc[5]); acc[6] = fmaf(gs, v.z, acc[6]); acc[7] = fmaf(gs, v.w, acc[7]);
+        }
+        float4* o4 = reinterpret_cast<float4*>(a.gY + g0 + r * 32 + 8 * q);
+        o4[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        o4[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+    __syncthreads();
+    if (live) {
+        const float* Yb = Ys + sl * n * 32 + 8 * q;
+        const float* gsc = gSs + sl * nn + j;
+#pragma unroll 2
+        for (int i = 0; i < n; ++i) {
+            const float gs = gsc[i * n];
+            const float4 u = lds128(Yb + i * 32), v = lds128(Yb + i * 32 + 4);
+            old[0] = fmaf(gs, u.x, old[0]); old[1] = fmaf(gs, u.y, old[1]); old[2] = fmaf(gs, u.z, old[2]); old[3] = fmaf(gs, u.w, old[3]);
+            old[4] = fmaf(gs, v.x, old[4]); old[5] = fmaf(gs, v.y, old[5]); old[6] = fmaf(gs, v.z, old[6]); old[7] = fmaf(gs, v.w, old[7]);
+        }
+        float4* o4 = reinterpret_cast<float4*>(a.gX + g0 + r * 32 + 8 * q);
+        o4[0] = make_float4(old[0], old[1], old[2], old[3]);
+        o4[1] = make_float4(old[4], old[5], old[6], old[7]);
+    }
+}
+
 // ---- temporal-difference loss of the value step (crowd_nav/utils/trainer.py:125-129) in one launch ---------------------
 //   target = reward + gamma_bar * V_next        (two rounded fp32 operations, like the tensor expression :126)
 //   loss  += sum_b (V - target)^2 * inv_count   (MSELoss(mean) over the GLOBAL batch: inv_count = 1 / global batch)
@@ -725,6 +882,29 @@ cudaError_t run_attn_layer_bwd(const float* A, const float* Hprev, const float* 
                                float* gA, int accumulate_gA, int B, int n, const float* mask, int up_rows, cudaStream_t st) {
     const long long threads = (long long)B * n * 4;
     attn_layer_bwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(A, Hprev, gM, gH, skip, gHprev, gA, accumulate_gA, B, n, mask, up_rows);
+    return cudaGetLastError();
+}
+
+cudaError_t run_attn_sim_bwd(const float* A, const float* Z, const float* gM, const float* mask, int up_rows, const float* gA_in,
+                             float* gZ, float* gA_out, const float* X, const float* Y, float* gY, float* gX, int gx_accumulate,
+                             int B, int n, size_t max_smem, cudaStream_t st) {
+    AttnSimArgs a;
+    a.A = A; a.Z = Z; a.gM = gM; a.mask = mask; a.gA_in = gA_in; a.X = X; a.Y = Y;
+    a.gZ = gZ; a.gA_out = gA_out; a.gY = gY; a.gX = gX;
+    a.up_rows = up_rows; a.gx_accumulate = gx_accumulate; a.B = B; a.n = n;
+    const bool sim = X != nullptr;
+    a.spb = 64 / n > 0 ? 64 / n : 1;              // spb * n rows x 4 threads <= 256
+    const int threads = ((a.spb * n * 4 + 31) / 32) * 32;
+    const size_t smem = ((size_t)a.spb * n * 32 * (sim ? 5 : 3) + (size_t)a.spb * n * n * (sim ? 3 : 2)) * sizeof(float);
+    if (smem > max_smem) return cudaErrorInvalidConfiguration;
+    const int grid = (B + a.spb - 1) / a.spb;
+    if (sim) {
+        if (cudaError_t e = ensure_dyn_smem(attn_sim_bwd_kernel<true>, (int)max_smem)) return e;
+        attn_sim_bwd_kernel<true><<<grid, threads, smem, st>>>(a);
+    } else {
+        if (cudaError_t e = ensure_dyn_smem(attn_sim_bwd_kernel<false>, (int)max_smem)) return e;
+        attn_sim_bwd_kernel<false><<<grid, threads, smem, st>>>(a);
+    }
     return cudaGetLastError();
 }
 

@@ -123,29 +123,41 @@ def _graph_backward(g, sv, robot, humans, gH, G, dev, top_rows=None):
     lib = _lib.lib()
     t = _carve([B * n * n, B * n * 32, B * n * 32, B * 64, B * Nh * 64] + [B * n * 32] * L, dev)
     gA, gM, gY, ga_r, ga_h = t[0].view(B, n, n), t[1].view(B, n, 32), t[2].view(B, n, 32), t[3].view(B, 64), t[4].view(B * Nh, 64)
-    for l in range(L - 1, -1, -1):
-        Hprev = sv['X'] if l == 0 else sv['Hl'][l - 1]
-        gHp = t[5 + l].view(B, n, 32)
-        if sv['tc']:
-            # H_l = relu(A Z) (+ H_{l-1}), Z = H_{l-1} W_l:   gZ = A^T (gH . mask),  gA (+)= (gH . mask) Z^T,
-            #                                                 dW_l = H_{l-1}^T gZ,    gH_{l-1} = gZ W_l^T (+ gH)
-            # (skip connection: gH has been consumed by the attention backward, so gZ W^T is accumulated into it in place)
-            _attn_bwd(sv['A'], sv['M'][l], gH, None, False, gM, gA, l != L - 1, B, n, dev, mask=sv['Rl'][l],
-                      up_rows=top_rows if l == L - 1 else None)
-            if skip:
-                gHp = gH
-            _linear_bwd(_rows(gM, 32), 32, _rows(Hprev, 32), 32, B * n, W=g.Ws[l], w_layout=1, Gin=_rows(gHp, 32), accumulate=skip,
-                        dW=G(g.Ws[l]), dev=dev)
-        else:
+    if sv['tc']:
+        # H_l = relu(A Z) (+ H_{l-1}), Z = H_{l-1} W_l:   gZ = A^T (gH . mask),  gA += (gH . mask) Z^T,
+        #                                                 dW_l = H_{l-1}^T gZ,    gH_{l-1} = gZ W_l^T (+ gH)
+        # One staged kernel per layer (rgl_attn_sim_bwd); at layer 0 it also runs the similarity backward, so gA never
+        # reaches memory there: it writes gY and the similarity term of gX, and the linear backward of W_0 accumulates
+        # onto it.  Skip connection: gH has been consumed by the staged kernel, gZ W^T is accumulated into it in place.
+        for l in range(L - 1, -1, -1):
+            Hprev = sv['X'] if l == 0 else sv['Hl'][l - 1]
+            sim = l == 0
+            gHp = gH if skip else t[5 + l].view(B, n, 32)
+            rc = lib.rgl_attn_sim_bwd(_lib.ptr(sv['A']), _lib.ptr(sv['M'][l]), _lib.ptr(gH), _lib.ptr(sv['Rl'][l]),
+                                      top_rows if (l == L - 1 and top_rows) else n, _lib.ptr(gA) if l != L - 1 else None,
+                                      _lib.ptr(gM), None if sim else _lib.ptr(gA),
+                                      _lib.ptr(sv['X']) if sim else None, _lib.ptr(sv['Y']) if sim else None,
+                                      _lib.ptr(gY) if sim else None, _lib.ptr(gHp) if sim else None, 1 if skip else 0,
+                                      B, n, _lib.stream_ptr(dev))
+            _lib.check(rc, 'rgl_attn_sim_bwd')
+            ops._count(1)
+            _linear_bwd(_rows(gM, 32), 32, _rows(Hprev, 32), 32, B * n, W=g.Ws[l], w_layout=1, Gin=_rows(gHp, 32),
+                        accumulate=skip or sim, dW=G(g.Ws[l]), dev=dev)
+            gH = gHp
+        gX = gH
+    else:
+        for l in range(L - 1, -1, -1):
+            Hprev = sv['X'] if l == 0 else sv['Hl'][l - 1]
+            gHp = t[5 + l].view(B, n, 32)
             _linear_bwd(_rows(gH, 32), 32, _rows(sv['M'][l], 32), 32, B * n, W=g.Ws[l], w_layout=1, mask=_rows(sv['Rl'][l], 32),
                         Gin=_rows(gM, 32), dW=G(g.Ws[l]), dev=dev)
             _attn_bwd(sv['A'], Hprev, gM, gH, skip, gHp, gA, l != L - 1, B, n, dev)
-        gH = gHp
-    gX = gH                                         # gradient w.r.t. X from the layer stack
-    rc = lib.rgl_sim_bwd(_lib.ptr(sv['A']), _lib.ptr(gA), _lib.ptr(sv['X']), _lib.ptr(sv['Y']), _lib.ptr(gY), _lib.ptr(gX),
-                         B, n, _lib.stream_ptr(dev))
-    _lib.check(rc, 'rgl_sim_bwd')
-    ops._count(1)
+            gH = gHp
+        gX = gH                                         # gradient w.r.t. X from the layer stack
+        rc = lib.rgl_sim_bwd(_lib.ptr(sv['A']), _lib.ptr(gA), _lib.ptr(sv['X']), _lib.ptr(sv['Y']), _lib.ptr(gY), _lib.ptr(gX),
+                             B, n, _lib.stream_ptr(dev))
+        _lib.check(rc, 'rgl_sim_bwd')
+        ops._count(1)
     _linear_bwd(_rows(gY, 32), 32, _rows(sv['X'], 32), 32, B * n, W=g.w_a, w_layout=1, Gin=_rows(gX, 32), accumulate=True,
                 dW=G(g.w_a), dev=dev)
     # embeddings: robot rows (node 0) and human rows (nodes 1..Nh) of gX, addressed in place as grouped rows.

@@ -150,3 +150,38 @@ def test_fused_td_loss_matches_torch(cuda_device):
     (3.0 * ref).backward()
     assert abs(float(loss) - float(ref)) <= 1e-6 * max(1.0, abs(float(ref)))
     assert torch.allclose(V.grad, V2.grad, rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize('n,B,up,sim,acc', [(11, 130, 11, True, True), (11, 64, 1, False, False), (6, 77, 6, True, False),
+                                            (21, 40, 21, False, True), (32, 9, 32, True, True), (1, 50, 1, True, False)])
+def test_staged_attn_sim_backward_matches_the_row_kernels(n, B, up, sim, acc, cuda_device):
+    """rgl_attn_sim_bwd (states staged in shared memory, similarity backward fused) against rgl_attn_layer_bwd + rgl_sim_bwd."""
+    from relationalgraphlearning_b200 import _lib
+    dev = cuda_device
+    gen = torch.Generator().manual_seed(n * 1000 + B)
+    rnd = lambda *s: torch.randn(*s, generator=gen).to(dev)   # noqa: E731
+    A = torch.softmax(rnd(B, n, n), dim=2).contiguous()
+    Z, gM, X, Y, mask = rnd(B, n, 32), rnd(B, n, 32), rnd(B, n, 32), rnd(B, n, 32), rnd(B, n, 32)
+    gM[:, up:, :] = 0                                         # the contract of up_rows
+    gA_in = rnd(B, n, n)
+    gX0 = rnd(B, n, 32)
+    lib, st, P = _lib.lib(), _lib.stream_ptr(dev), _lib.ptr
+    with torch.cuda.device(dev):
+        # row kernels
+        gZ_ref, gA_ref = torch.empty_like(Z), (gA_in.clone() if acc else torch.empty_like(gA_in))
+        _lib.check(lib.rgl_attn_layer_bwd(P(A), P(Z), P(gM), None, 0, P(gZ_ref), P(gA_ref), 1 if acc else 0, B, n, P(mask), n, st), 'attn')
+        gY_ref, gX_ref = torch.empty_like(X), gX0.clone()
+        if sim:
+            _lib.check(lib.rgl_sim_bwd(P(A), P(gA_ref), P(X), P(Y), P(gY_ref), P(gX_ref), B, n, st), 'sim')
+        # staged kernel
+        gZ, gA_out, gY, gX = torch.empty_like(Z), torch.full_like(gA_in, float('nan')), torch.empty_like(X), gX0.clone()
+        _lib.check(lib.rgl_attn_sim_bwd(P(A), P(Z), P(gM), P(mask), up, P(gA_in) if acc else None, P(gZ), None if sim else P(gA_out),
+                                        P(X) if sim else None, P(Y) if sim else None, P(gY) if sim else None, P(gX) if sim else None,
+                                        1, B, n, st), 'attn_sim')
+    torch.cuda.synchronize(dev)
+    assert_close_scaled(gZ, gZ_ref, 1e-5, 'gZ')
+    if sim:
+        assert_close_scaled(gY, gY_ref, 1e-5, 'gY')
+        assert_close_scaled(gX, gX_ref, 1e-5, 'gX')
+    else:
+        assert_close_scaled(gA_out, gA_ref, 1e-5, 'gA')
