@@ -9,34 +9,9 @@
 //   sim_bwd           A = softmax(Y X^T):  gS, gY = gS X, gX += gS^T Y            (per state)
 #include <stdlib.h>
 #include "kernels.h"
+#include "train_common.cuh"
 
 namespace rgl {
-
-// row r of a logical [R, width] matrix: ptr + (r / rpg) * gstride + (r % rpg) * ld   (grouped rows: e.g. the robot
-// row of every state inside a [B, n, 32] tensor is rpg = 1, gstride = n*32)
-struct Rows {
-    float* ptr;
-    int ld;
-    int rpg;
-    long long gstride;
-    __device__ __forceinline__ float* row(int r) const {
-        if (rpg == 1) return ptr + (long long)r * gstride;              // plain matrix / one row per group: no division
-        return ptr + (long long)(r / rpg) * gstride + (long long)(r % rpg) * ld;
-    }
-};
-
-struct LinBwdArgs {
-    Rows G, mask, Xin, Gin;
-    int N, K, R;
-    const float* W;       // optional (data gradient)
-    int w_layout;         // 0: W is [N][K] (nn.Linear.weight), 1: W is [K][N] (w_a / Ws used as x @ W)
-    int accumulate;       // Gin += instead of =
-    float* dW;            // optional, same layout as W
-    float* db;            // optional [N]
-    int ntiles;
-    int vecG, vecX;       // rows of G(+mask) / Xin are 16-byte aligned and N / K are multiples of 4
-    int vecW;             // W is [N][K] with K a multiple of 4 and a 16-byte aligned base: staged with cp.async
-};
 
 constexpr int LT = 64;    // rows per tile
 
@@ -857,8 +832,13 @@ cudaError_t run_linear_bwd(const RglRows* G, int N, const RglRows* mask, const R
     a.vecG = vec_ok(a.G, N) && (a.mask.ptr == nullptr || vec_ok(a.mask, N));
     a.vecX = vec_ok(a.Xin, K);
     a.vecW = W != nullptr && w_layout == 0 && (K & 3) == 0 && (reinterpret_cast<uintptr_t>(W) & 15u) == 0;
-    // N, K <= 64: tensor-core kernel (mma.sync 3xTF32).  RGL_BWD_VARIANT=f keeps the fp32-FMA kernel (experiments only).
+    // N = 32, K = 32 / 64: tcgen05 kernel (linear_bwd_tc.cu); other shapes: mma.sync 3xTF32 kernel below.
+    // RGL_BWD_VARIANT (experiments only): t = tcgen05 wherever it applies, m = mma.sync for every shape, f = fp32-FMA kernel.
     static const char* variant = getenv("RGL_BWD_VARIANT");
+    if (!variant || variant[0] == 't') {
+        const cudaError_t e = run_linear_bwd_tc(a, num_sms, max_smem, st);
+        if (e != cudaErrorNotSupported && e != cudaErrorInvalidConfiguration) return e;
+    }
     if (!(variant && variant[0] == 'f')) {
         const cudaError_t e = dispatch_bwd_mma(a, num_sms, max_smem, st);
         if (e != cudaErrorNotSupported && e != cudaErrorInvalidConfiguration) return e;

@@ -25,7 +25,7 @@ def build(seed, dev, **kw):
     return ve, sd_g, sd_v
 
 
-@pytest.mark.parametrize('nh,B,kw', [(5, 64, {}), (5, 100, {}), (10, 257, {}), (20, 33, {}), (3, 50, {}),
+@pytest.mark.parametrize('nh,B,kw', [(5, 64, {}), (5, 100, {}), (10, 257, {}), (20, 33, {}), (3, 50, {}), (10, 2048, {}),
                                      (5, 64, dict(num_layer=1)), (5, 64, dict(num_layer=3)), (5, 96, dict(skip_connection=False))])
 def test_native_backward_matches_oracle_autograd(nh, B, kw, cuda_device):
     ve, sd_g, sd_v = build(7, cuda_device, **kw)
@@ -185,3 +185,52 @@ def test_staged_attn_sim_backward_matches_the_row_kernels(n, B, up, sim, acc, cu
         assert_close_scaled(gX, gX_ref, 1e-5, 'gX')
     else:
         assert_close_scaled(gA_out, gA_ref, 1e-5, 'gA')
+
+
+_TC_BWD_SCRIPT = r"""
+import sys, torch
+sys.path.insert(0, %r)
+from relationalgraphlearning_b200 import training as T
+dev = torch.device('cuda:0')
+torch.manual_seed(5)
+worst = 0.0
+# (rows, K, layout, mask, bias, accumulate, grouped): N = 32 always (the tcgen05 kernel's shapes)
+for R, K, layout, mask, bias, accum, grouped in [(1000, 32, 1, False, False, True, False), (333, 32, 0, True, True, False, False),
+                                                 (4100, 64, 0, True, True, False, True), (129, 64, 1, False, False, True, False),
+                                                 (20000, 32, 1, False, False, True, False)]:
+    n = 11
+    if grouped:      # rows 1..n-1 of every state of a [B, n, .] tensor (the human rows)
+        Bq = R // (n - 1); R = Bq * (n - 1)
+        Gf, Mf, Xf = torch.randn(Bq, n, 32, device=dev), torch.randn(Bq, n, 32, device=dev), torch.randn(Bq, n, K, device=dev)
+        G, M, X = Gf[:, 1:].reshape(R, 32), Mf[:, 1:].reshape(R, 32), Xf[:, 1:].reshape(R, K)
+        rG, rM, rX = T._rows(Gf, 32, n - 1, n * 32, offset=32), T._rows(Mf, 32, n - 1, n * 32, offset=32), T._rows(Xf, K, n - 1, n * K, offset=K)
+    else:
+        G, M, X = torch.randn(R, 32, device=dev), torch.randn(R, 32, device=dev), torch.randn(R, K, device=dev)
+        rG, rM, rX = T._rows(G, 32), T._rows(M, 32), T._rows(X, K)
+    W = torch.randn(32, K, device=dev) if layout == 0 else torch.randn(K, 32, device=dev)
+    Gin0 = torch.randn(R, K, device=dev)
+    Gin, dW, db = Gin0.clone(), torch.zeros_like(W), torch.zeros(32, device=dev)
+    T._linear_bwd(rG, 32, rX, K, R, W=W, w_layout=layout, mask=rM if mask else None, Gin=T._rows(Gin, K), accumulate=accum,
+                  dW=dW, db=db if bias else None, dev=dev)
+    torch.cuda.synchronize()
+    Gm = (G * (M > 0)) if mask else G
+    Gd, Xd, Wd = Gm.double(), X.double(), W.double()
+    ref_in = (Gd @ Wd) if layout == 0 else (Gd @ Wd.t())
+    if accum: ref_in = ref_in + Gin0.double()
+    ref_dW = (Gd.t() @ Xd) if layout == 0 else (Xd.t() @ Gd)
+    for got, ref in ((Gin, ref_in), (dW, ref_dW)) + (((db, Gd.sum(0)),) if bias else ()):
+        worst = max(worst, float((got.double() - ref).abs().max() / ref.abs().max()))
+print('WORST %%.3e' %% worst)
+"""
+
+
+def test_tcgen05_linear_backward_forced_on_every_shape(cuda_device):
+    """linear_bwd_tc.cu takes only the big K = 32 launches by default; RGL_BWD_VARIANT=t (read once per process, hence the
+    subprocess) runs it on K = 32 / 64, with mask, bias, += and grouped rows, against float64 matmuls."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RGL_BWD_VARIANT='t')
+    out = subprocess.run([sys.executable, '-c', _TC_BWD_SCRIPT % root], env=env, capture_output=True, text=True, timeout=280)
+    assert out.returncode == 0, out.stderr[-2000:]
+    worst = float(out.stdout.strip().split('WORST')[-1])
+    assert worst < 2e-6, out.stdout                       # 3xTF32: fp32-level agreement with the float64 reference

@@ -527,6 +527,115 @@ static void run_rate() {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// MN-major probe (the weight-gradient shape): D[M][32] = sum_r A[r][m] * G[r][n], contraction over the 128 ROWS of the tile.
+//   A: M/32 tiles [128 rows][32 floats], G: one tile [128][32]; every tile is 128-byte rows, SWIZZLE_128B (chunk ^ (row & 7)),
+//   8-row groups of 1024 B -- the layout a TMA SWIZZLE_128B load of a row-major [rows][32] fp32 matrix produces.
+//   Descriptors: LBO = distance between the M atoms (tiles), SBO = 1024 (next 8 rows); one MMA (K = 8) per 8-row group.
+//   idesc: a_major (bit 15) = b_major (bit 16) = 1 (MN-major).
+// Dumps all 128 TMEM lanes so that the host can find where each D row lands (M = 64 uses a subset of the lanes).
+__device__ __forceinline__ uint32_t sw128_32(int r, int c16) {
+    return (uint32_t)r * 128u + (uint32_t)((((c16 >> 1) ^ r) & 3) << 5) + (uint32_t)((c16 & 1) << 4);
+}
+template <int M>
+__global__ void __launch_bounds__(128) mn_probe(const float* __restrict__ A, const float* __restrict__ G, float* __restrict__ D, int lbo_mode) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int MA = M / 32;
+    uint8_t* At = smem;                     // MA x 16 KB
+    uint8_t* Gt = At + MA * 16384;
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tslot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) tmem_alloc(&tslot, 32);
+    if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = tslot;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    {   // zero the accumulator lanes first (lanes an M = 64 MMA does not touch then read back as 0)
+        uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int c = 0; c < 4; ++c) tmem_st8(tbase + lane_base + 8 * c, z);
+        tmem_st_wait();
+    }
+    for (int ma = 0; ma < MA; ++ma)
+        for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<float4*>(At + ma * 16384 + sw128_32(tid, c)) = *reinterpret_cast<const float4*>(A + tid * M + ma * 32 + c * 4);
+    for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<float4*>(Gt + sw128_32(tid, c)) = *reinterpret_cast<const float4*>(G + tid * 32 + c * 4);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+        tc_fence_after();
+        const uint32_t idesc = make_idesc(M, 32) | (1u << 15) | (1u << 16);
+        for (int ks = 0; ks < 16; ++ks) {
+            uint64_t ad = 0, bd = 0;
+            const uint32_t aaddr = smem_u32(At) + ks * 1024, baddr = smem_u32(Gt) + ks * 1024;
+            // MN-major tf32: SWIZZLE_128B_BASE32B (layout type 1) is the only swizzled layout: 128-byte rows, 4-row atoms of 512 B,
+            // 32-byte chunks XOR-ed with (row & 3).  LBO = distance between the MN atoms, SBO = distance between 4-row groups.
+            const uint32_t lbo = lbo_mode == 0 ? 16384u : 512u, sbo = lbo_mode == 0 ? 512u : 16384u;
+            ad = (uint64_t)((aaddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
+            bd = (uint64_t)((baddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
+            umma_tf32_ss(tbase, ad, bd, idesc, ks > 0);
+        }
+        umma_commit(&bar);
+    }
+    mbar_wait(&bar, 0);
+    tc_fence_after();
+    float v[32];
+    tmem_ld32(tbase + lane_base, v);
+    for (int j = 0; j < 32; ++j) D[tid * 32 + j] = v[j];
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, 32);
+}
+
+template <int M>
+static int run_mn(int lbo_mode) {
+    std::vector<float> A(128 * M), G(128 * 32), D(128 * 32);
+    srand(77);
+    for (auto& v : A) v = (float)(rand() % 17 - 8);          // small integers: exact in tf32
+    for (auto& v : G) v = (float)(rand() % 13 - 6);
+    float *dA, *dG, *dD;
+    CK(cudaMalloc(&dA, A.size() * 4)); CK(cudaMalloc(&dG, G.size() * 4)); CK(cudaMalloc(&dD, D.size() * 4));
+    CK(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dG, G.data(), G.size() * 4, cudaMemcpyHostToDevice));
+    const size_t smem = 1024 + (M / 32 + 1) * 16384;
+    CK(cudaFuncSetAttribute(mn_probe<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mn_probe<M><<<1, 128, smem>>>(dA, dG, dD, lbo_mode);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+    std::vector<float> ref(M * 32);
+    for (int m = 0; m < M; ++m)
+        for (int n = 0; n < 32; ++n) {
+            float acc = 0.f;
+            for (int r = 0; r < 128; ++r) acc += A[r * M + m] * G[r * 32 + n];
+            ref[m * 32 + n] = acc;
+        }
+    // where does each expected row land?
+    int found = 0;
+    printf("MN-major probe M=%d lbo_mode=%d: row -> lane map:", M, lbo_mode);
+    for (int m = 0; m < M; ++m) {
+        int at = -1;
+        for (int l = 0; l < 128 && at < 0; ++l) {
+            bool same = true;
+            for (int n = 0; n < 32 && same; ++n) same = D[l * 32 + n] == ref[m * 32 + n];
+            if (same) at = l;
+        }
+        if (at >= 0) ++found;
+        if (m % 8 == 0) printf(" [%d]->%d", m, at);
+    }
+    int nonzero_lanes = 0;
+    for (int l = 0; l < 128; ++l) { bool nz = false; for (int n = 0; n < 32; ++n) nz |= D[l * 32 + n] != 0.f; nonzero_lanes += nz; }
+    printf("\n  rows found %d / %d, non-zero lanes %d;  D[lane0][0..3] = %g %g %g %g  ref[0][0..3] = %g %g %g %g\n", found, M, nonzero_lanes,
+           D[0], D[1], D[2], D[3], ref[0], ref[1], ref[2], ref[3]);
+    printf("MN-major probe M=%d lbo_mode=%d: %s\n", M, lbo_mode, found == M ? "PASS" : "FAIL");
+    return found == M ? 0 : 1;
+}
+
 int main(int argc, char** argv) {
     const int test = argc > 1 ? atoi(argv[1]) : 1;
     switch (test) {
@@ -540,6 +649,7 @@ int main(int argc, char** argv) {
                 run_rate2<64, true, 8>(); run_rate2<64, true, 15>(); run_rate2<32, true, 15>(); return 0;
         case 10: run_rate3<64, 1>(); run_rate3<64, 2>(); run_rate3<64, 4>(); run_rate3<32, 4>(); run_rate3<128, 1>(); run_rate3<256, 1>(); return 0;
         case 11: run_rate2<32, true, 0, true>(); run_rate2<64, true, 0, true>(); run_rate2<32, true, 0, false>(); run_rate2<128, true, 0, true>(); return 0;
+        case 12: { int rc = run_mn<128>(0); rc |= run_mn<64>(0); return rc; }
         case 6: return run_gemm<32, 64, 1>("3xTF32 SS K=32 N=64");
         case 7: return run_gemm<64, 32, 1>("3xTF32 SS K=64 N=32");
     }
