@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define RGL_B200_VERSION 201          /* major*10000 + minor*100 + patch */
+#define RGL_B200_VERSION 202          /* major*10000 + minor*100 + patch */
 
 #define RGL_X_DIM        32           /* config.gcn.X_dim = final_state_dim (configs/icra_benchmark/config.py:103-108) */
 #define RGL_EMB_HIDDEN   64           /* wr_dims[0] = wh_dims[0] */
@@ -214,6 +214,12 @@ int rgl_value_head_train(const float* E, int B, const float* value_packed, float
 int rgl_linear_bwd(const RglRows* G, int N, const RglRows* mask, const RglRows* Xin, int K,
                    const float* W, int w_layout, const RglRows* Gin, int accumulate,
                    float* dW, float* db, int R, rgl_stream_t stream);
+/* Backward of BOTH Linear layers of a two-layer embedding MLP  x0 [R,K0] -> relu -> hidden [R,64] -> relu -> X [R,32]
+ * (w_r / w_h, crowd_nav/policy/graph_model.py:41-42) in one launch; the hidden layer's gradient never reaches memory:
+ *   G = gX . (mask > 0);  dW1 [32,64] += G^T hidden;  db1 [32] += colsum G;
+ *   Hg = (G W1) . (hidden > 0);  dW0 [64,K0] += Hg^T x0;  db0 [64] += colsum Hg.        K0 <= 16; accumulators ATOMIC (zero first). */
+int rgl_mlp2_bwd(const RglRows* G, const RglRows* mask, const RglRows* hidden, const float* W1, const RglRows* X0, int K0,
+                 float* dW1, float* db1, float* dW0, float* db0, int R, rgl_stream_t stream);
 /* gHprev[b,j,:] = (skip ? gH[b,j,:] : 0) + sum_i A[b,i,j] gM[b,i,:];  gA[b,i,j] (+)= gM[b,i,:] . Hprev[b,j,:]
  * mask (optional, [B,n,32]): gM is multiplied by (mask > 0) on load.
  * up_rows in [1,n]: only node rows i < up_rows of gM carry gradient; the others are taken as zero and never read

@@ -74,6 +74,8 @@ EXPORTS = {
     'rgl_linear_bwd': (ctypes.c_int, [ctypes.POINTER(Rows), ctypes.c_int, ctypes.POINTER(Rows), ctypes.POINTER(Rows), ctypes.c_int,
                                       c_float_p, ctypes.c_int, ctypes.POINTER(Rows), ctypes.c_int, c_float_p, c_float_p,
                                       ctypes.c_int, ctypes.c_void_p]),
+    'rgl_mlp2_bwd': (ctypes.c_int, [ctypes.POINTER(Rows), ctypes.POINTER(Rows), ctypes.POINTER(Rows), c_float_p, ctypes.POINTER(Rows),
+                                    ctypes.c_int, c_float_p, c_float_p, c_float_p, c_float_p, ctypes.c_int, ctypes.c_void_p]),
     'rgl_attn_layer_bwd': (ctypes.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, ctypes.c_int, c_float_p, c_float_p,
                                           ctypes.c_int, ctypes.c_int, ctypes.c_int, c_float_p, ctypes.c_int, ctypes.c_void_p]),
     'rgl_attn_sim_bwd': (ctypes.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, ctypes.c_int, c_float_p, c_float_p, c_float_p,

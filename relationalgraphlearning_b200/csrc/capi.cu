@@ -271,6 +271,19 @@ int rgl_linear_bwd(const RglRows* G, int N, const RglRows* mask, const RglRows* 
     return e == cudaSuccess ? RGL_OK : fail_cuda(e, "rgl_linear_bwd");
 }
 
+int rgl_mlp2_bwd(const RglRows* G, const RglRows* mask, const RglRows* hidden, const float* W1, const RglRows* X0, int K0,
+                 float* dW1, float* db1, float* dW0, float* db0, int R, rgl_stream_t stream) {
+    if (R == 0) return RGL_OK;
+    if (!G || !G->ptr || !hidden || !hidden->ptr || !X0 || !X0->ptr || !W1 || !dW1 || !dW0 || R < 0)
+        return fail(RGL_EINVAL, "rgl_mlp2_bwd: bad argument");
+    if (K0 < 1 || K0 > 16) return fail(RGL_EUNSUPPORTED, "rgl_mlp2_bwd: K0 must be in [1,16]");
+    DevInfo d;
+    if (int rc = dev_info(&d)) return rc;
+    cudaError_t e = rgl::run_mlp2_bwd(G, mask, hidden, W1, X0, K0, dW1, db1, dW0, db0, R, d.sms, d.max_smem, (cudaStream_t)stream);
+    if (e == cudaErrorNotSupported) return fail(RGL_EUNSUPPORTED, "rgl_mlp2_bwd: shape not supported");
+    return e == cudaSuccess ? RGL_OK : fail_cuda(e, "rgl_mlp2_bwd");
+}
+
 int rgl_attn_layer_bwd(const float* A, const float* Hprev, const float* gM, const float* gH, int skip, float* gHprev, float* gA,
                        int accumulate_gA, int B, int n, const float* mask, int up_rows, rgl_stream_t stream) {
     if (B == 0) return RGL_OK;

@@ -89,6 +89,8 @@ cudaError_t run_value_head_tc_train(const float* E, int B, const float* vw, floa
 cudaError_t run_linear_bwd(const RglRows* G, int N, const RglRows* mask, const RglRows* Xin, int K, const float* W, int w_layout,
                            const RglRows* Gin, int accumulate, float* dW, float* db, int R, int num_sms, size_t max_smem,
                            cudaStream_t st);
+cudaError_t run_mlp2_bwd(const RglRows* G, const RglRows* mask, const RglRows* hidden, const float* W1, const RglRows* X0, int K0,
+                         float* dW1, float* db1, float* dW0, float* db0, int R, int num_sms, size_t max_smem, cudaStream_t st);
 cudaError_t run_attn_layer_bwd(const float* A, const float* Hprev, const float* gM, const float* gH, int skip, float* gHprev,
                                float* gA, int accumulate_gA, int B, int n, const float* mask, int up_rows, cudaStream_t st);
 cudaError_t run_attn_sim_bwd(const float* A, const float* Z, const float* gM, const float* mask, int up_rows, const float* gA_in,

@@ -28,6 +28,11 @@ struct LinBwdArgs {
     int ntiles;
     int vecG, vecX;       // rows of G(+mask) / Xin are 16-byte aligned and N / K are multiples of 4
     int vecW;             // W is [N][K] with K a multiple of 4 and a 16-byte aligned base: staged with cp.async
+    // fused first layer of a two-layer MLP (rgl_mlp2_bwd): x0 rows [R, K0], dW0 [K][K0] (nn.Linear layout), db0 [K]
+    Rows X0;
+    int K0;
+    float* dW0;
+    float* db0;
 };
 
 // tcgen05 form of the backward for the 32-wide layers (linear_bwd_tc.cu); cudaErrorNotSupported: shape / layout not covered

@@ -216,7 +216,11 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // Every shape parameter is a template argument (N8 = ceil(N/8), K16 = ceil(K/16)): the first version took them at run time
 // and spent 95 % of its instructions on index arithmetic (ncu: 2 550 warp instructions per warp and tile for 96 HMMA,
 // instruction-cache hit rate 80 %).
-template <int N8, int K16, int MROWS, bool DB>
+// F0 (fused first layer of a two-layer MLP, K = 64): the data gradient G W is not written to memory; it is multiplied by
+// (Xin > 0) -- Xin is the hidden activation relu(x0 W0^T + b0) -- in place in the staged Xin tile and contracted with the
+// MLP input x0 (a.X0, K0 <= 16 columns) right here: dW0 += (G W . (Xin > 0))^T x0, db0 += its column sums.  One launch
+// and one pass over the rows for both Linear layers of w_r / w_h (graph_model.py:41-42).
+template <int N8, int K16, int MROWS, bool DB, bool F0 = false>
 __global__ void __launch_bounds__(256, (DB || MROWS <= 32) ? 2 : 1) rows_linear_bwd_mma_kernel(const LinBwdArgs a) {
     extern __shared__ __align__(128) float smem[];
     constexpr int NP = N8 * 8, KP = K16 * 16, K8 = K16 * 2;
@@ -224,7 +228,8 @@ __global__ void __launch_bounds__(256, (DB || MROWS <= 32) ? 2 : 1) rows_linear_
     constexpr int WPR = 8 / (MROWS / 16);   // warps sharing a 16-row block in the data gradient (1 or 2): they split the k columns
     constexpr int KPW = (K8 + WPR - 1) / WPR;                // k column tiles per warp in the data gradient
     constexpr int WT = K16 * N8, TW = (WT + 7) / 8;          // (16 x 8) tiles of dW; tile id = warp + 8 i
-    constexpr int tileG = MROWS * ldg, tileX = MROWS * ldx, stage_floats = 2 * tileG + tileX;
+    constexpr int ld0 = 24;                                  // x0 tile: 16 columns (K0 <= 16, zero padded), stride = 24 mod 32 words
+    constexpr int tileG = MROWS * ldg, tileX = MROWS * ldx, tile0 = F0 ? MROWS * ld0 : 0, stage_floats = 2 * tileG + tileX + tile0;
     constexpr int n4 = NP / 4, k4 = KP / 4;
     const int N = a.N, K = a.K;
     float* Ws = smem;                       // [NP][ldx]   Ws[n][k]
@@ -261,6 +266,13 @@ __global__ void __launch_bounds__(256, (DB || MROWS <= 32) ? 2 : 1) rows_linear_
 #pragma unroll
         for (int c = 0; c < 4; ++c) wacc[i][c] = 0.f;
     float bacc = 0.f;
+    float w0acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};      // F0: dW0 fragment (16 hidden units x 16 input columns)
+    float bacc0 = 0.f;
+    if (F0) {                                                // columns K0..15 of the x0 tiles stay zero for the whole kernel
+        for (int st = 0; st < (DB ? 2 : 1); ++st)
+            for (int i = tid; i < tile0; i += 256) Gs0[st * stage_floats + 2 * tileG + tileX + i] = 0.f;
+        __syncthreads();
+    }
 
     // issue the copies of one tile into stage `st` (vector path: cp.async; otherwise plain loads / stores by the same thread)
     auto stage = [&](int tile, int st) {
@@ -308,6 +320,15 @@ __global__ void __launch_bounds__(256, (DB || MROWS <= 32) ? 2 : 1) rows_linear_
                 }
             }
         }
+        if (F0) {
+            float* X0s = Xs + tileX;
+            for (int idx = tid; idx < MROWS * a.K0; idx += 256) {
+                const int r = idx / a.K0, c = idx - r * a.K0;
+                const bool in = r0 + r < a.R;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(smem_u32(X0s + r * ld0 + c)),
+                             "l"(in ? a.X0.row(r0 + r) + c : a.X0.ptr), "r"(in ? 4u : 0u) : "memory");
+            }
+        }
         cp_async_commit();
     };
 
@@ -338,7 +359,8 @@ __global__ void __launch_bounds__(256, (DB || MROWS <= 32) ? 2 : 1) rows_linear_
         __syncthreads();
 
         // ---- data gradient: a warp owns 16 rows (x a share of the k columns when two warps split a row block) ----
-        if (a.W && a.Gin.ptr) {
+        auto data_grad = [&]() {
+        if (a.W && (F0 || a.Gin.ptr)) {
             const int rb = warp / WPR, part = warp - rb * WPR;
             const int nt0 = part * KPW;
             float acc[KPW][4];
@@ -368,6 +390,23 @@ __global__ void __launch_bounds__(256, (DB || MROWS <= 32) ? 2 : 1) rows_linear_
                     }
                 }
             }
+            if (F0) {
+                // the hidden layer's gradient stays on chip: masked with (hidden activation > 0) it replaces that activation
+                // in the staged tile (each element is read and overwritten by the one thread that owns it; the weight
+                // gradient that needs the activation has already run)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    float* o = Xs + (rb * 16 + g + 8 * q) * ldx + nt0 * 8 + 2 * t;
+#pragma unroll
+                    for (int nt = 0; nt < KPW; ++nt) {
+                        if (WPR == 1 || nt0 + nt < K8) {
+                            const float2 h = *reinterpret_cast<const float2*>(o + nt * 8);
+                            *reinterpret_cast<float2*>(o + nt * 8) = make_float2(h.x > 0.f ? acc[nt][2 * q] : 0.f, h.y > 0.f ? acc[nt][2 * q + 1] : 0.f);
+                        }
+                    }
+                }
+                return;
+            }
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
                 const int r = r0 + rb * 16 + g + 8 * q;
@@ -389,7 +428,9 @@ __global__ void __launch_bounds__(256, (DB || MROWS <= 32) ? 2 : 1) rows_linear_
                 }
             }
         }
+        };
         // ---- weight gradient: the rows of the tile are the contraction ----
+        auto weight_grad = [&]() {
         if (a.dW) {
 #pragma unroll
             for (int i = 0; i < TW; ++i) {
@@ -434,6 +475,49 @@ __global__ void __launch_bounds__(256, (DB || MROWS <= 32) ? 2 : 1) rows_linear_
             }
             bacc += (s0 + s1) + (s2 + s3);
         }
+        };
+        if (!F0) {
+            data_grad();
+            weight_grad();
+        } else {
+            weight_grad();                      // needs the hidden activation tile ...
+            __syncthreads();
+            data_grad();                        // ... which the masked hidden gradient then replaces
+            __syncthreads();
+            // first layer: dW0[m][c] += sum_rows Hg[row][m] x0[row][c]; warp = (16 hidden units, half of the rows)
+            {
+                const float* X0s = Xs + tileX;
+                const int mt = warp & 3, kh = warp >> 2;
+                const float* hp = Xs + t * ldx + mt * 16 + g;
+                const float* xq = X0s + t * ld0 + g;
+#pragma unroll 2
+                for (int ks = kh * (MROWS / 16); ks < (kh + 1) * (MROWS / 16); ++ks) {
+                    uint32_t ahi[4], alo[4];
+                    split_tf32(hp[(ks * 8) * ldx], ahi[0], alo[0]);
+                    split_tf32(hp[(ks * 8) * ldx + 8], ahi[1], alo[1]);
+                    split_tf32(hp[(ks * 8 + 4) * ldx], ahi[2], alo[2]);
+                    split_tf32(hp[(ks * 8 + 4) * ldx + 8], ahi[3], alo[3]);
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt) {
+                        if (nt * 8 < a.K0) {
+                            uint32_t bh0, bl0, bh1, bl1;
+                            split_tf32(xq[(ks * 8) * ld0 + nt * 8], bh0, bl0);
+                            split_tf32(xq[(ks * 8 + 4) * ld0 + nt * 8], bh1, bl1);
+                            mma_tf32(w0acc[nt], alo, bh0, bh1);
+                            mma_tf32(w0acc[nt], ahi, bl0, bl1);
+                            mma_tf32(w0acc[nt], ahi, bh0, bh1);
+                        }
+                    }
+                }
+                if (tid < 128) {                // db0: column sums of the masked hidden gradient, half of the rows each
+                    const float* hc = Xs + (tid >> 6) * (MROWS / 2) * ldx + (tid & 63);
+                    float s0 = 0.f, s1 = 0.f;
+#pragma unroll 4
+                    for (int r = 0; r < MROWS / 2; r += 2) { s0 += hc[r * ldx]; s1 += hc[(r + 1) * ldx]; }
+                    bacc0 += s0 + s1;
+                }
+            }
+        }
         __syncthreads();                    // every warp is done with this stage before it is refilled
         if (!DB && next < a.ntiles) stage(next, 0);
     }
@@ -453,26 +537,37 @@ __global__ void __launch_bounds__(256, (DB || MROWS <= 32) ? 2 : 1) rows_linear_
         }
     }
     if (a.db && (tid & 127) < N) atomicAdd(a.db + (tid & 127), bacc);
+    if (F0) {
+        const int mt = warp & 3;
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int m = mt * 16 + g + 8 * (c >> 1), col = nt * 8 + 2 * t + (c & 1);
+                if (col < a.K0) atomicAdd(a.dW0 + (size_t)m * a.K0 + col, w0acc[nt][c]);
+            }
+        if (a.db0 && tid < 128) atomicAdd(a.db0 + (tid & 63), bacc0);
+    }
 }
 
-template <int N8, int K16, int MROWS, bool DB>
+template <int N8, int K16, int MROWS, bool DB, bool F0 = false>
 static cudaError_t launch_bwd_mma(LinBwdArgs& a, int num_sms, size_t max_smem, cudaStream_t st) {
     constexpr int NP = N8 * 8, KP = K16 * 16;
     constexpr int ldg = ((NP + 31) / 32) * 32 + 8, ldx = ((KP + 31) / 32) * 32 + 8;
-    constexpr size_t stage = (size_t)2 * MROWS * ldg + (size_t)MROWS * ldx;
+    constexpr size_t stage = (size_t)2 * MROWS * ldg + (size_t)MROWS * ldx + (F0 ? (size_t)MROWS * 24 : 0);
     constexpr size_t sm = ((size_t)NP * ldx + stage * (DB ? 2 : 1)) * sizeof(float);
     static_assert(sm <= 227 * 1024, "staging tiles exceed the shared memory of an SM");
     if (sm > max_smem) return cudaErrorInvalidConfiguration;
-    if (cudaError_t e = ensure_dyn_smem(rows_linear_bwd_mma_kernel<N8, K16, MROWS, DB>, (int)max_smem)) return e;
+    if (cudaError_t e = ensure_dyn_smem(rows_linear_bwd_mma_kernel<N8, K16, MROWS, DB, F0>, (int)max_smem)) return e;
     a.ntiles = (a.R + MROWS - 1) / MROWS;
     int per_sm = (int)((227 * 1024) / (sm + 1024));
     // registers: __launch_bounds__(256, 2) guarantees two CTAs per SM; a third fits when the kernel needs <= 85 registers
     cudaFuncAttributes fa;
     int reg_cap = (DB || MROWS <= 32) ? 2 : 1;
-    if (DB && cudaFuncGetAttributes(&fa, rows_linear_bwd_mma_kernel<N8, K16, MROWS, DB>) == cudaSuccess && fa.numRegs * 256 * 3 <= 65536) reg_cap = 3;
+    if (DB && cudaFuncGetAttributes(&fa, rows_linear_bwd_mma_kernel<N8, K16, MROWS, DB, F0>) == cudaSuccess && fa.numRegs * 256 * 3 <= 65536) reg_cap = 3;
     per_sm = per_sm < 1 ? 1 : (per_sm > reg_cap ? reg_cap : per_sm);
     const int cap = num_sms * per_sm;
-    rows_linear_bwd_mma_kernel<N8, K16, MROWS, DB><<<a.ntiles < cap ? a.ntiles : cap, 256, sm, st>>>(a);
+    rows_linear_bwd_mma_kernel<N8, K16, MROWS, DB, F0><<<a.ntiles < cap ? a.ntiles : cap, 256, sm, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -485,6 +580,11 @@ static cudaError_t dispatch_bwd_mma(LinBwdArgs& a, int num_sms, size_t max_smem,
         RGL_BWD_CASE(4, 2, 128, true);
         RGL_BWD_CASE(4, 4, 128, true);
         RGL_BWD_CASE(8, 1, 128, true);
+    }
+    if (a.dW0) {                        // fused two-layer MLP backward (w_r / w_h): N = 32, K = 64
+        if (N8 != 4 || K16 != 4 || a.K != 64 || a.K0 < 1 || a.K0 > 16 || !a.W || !a.X0.ptr) return cudaErrorNotSupported;
+        if ((a.R + 63) / 64 <= num_sms) return launch_bwd_mma<4, 4, 32, true, true>(a, num_sms, max_smem, st);
+        return launch_bwd_mma<4, 4, 64, true, true>(a, num_sms, max_smem, st);
     }
     if ((a.R + 63) / 64 <= num_sms) {
         // fewer 64-row tiles than SMs (the B-row layers: value head, robot embedding): 32-row tiles double the CTAs and the
@@ -826,6 +926,7 @@ cudaError_t run_linear_bwd(const RglRows* G, int N, const RglRows* mask, const R
     LinBwdArgs a;
     a.G = to_rows(G); a.mask = to_rows(mask); a.Xin = to_rows(Xin); a.Gin = to_rows(Gin);
     a.N = N; a.K = K; a.R = R; a.W = W; a.w_layout = w_layout; a.accumulate = accumulate; a.dW = dW; a.db = db;
+    a.X0 = to_rows(nullptr); a.K0 = 0; a.dW0 = nullptr; a.db0 = nullptr;
     auto vec_ok = [](const Rows& r, int width) {
         return r.ptr != nullptr && (reinterpret_cast<uintptr_t>(r.ptr) & 15u) == 0 && (r.ld & 3) == 0 && (r.gstride & 3) == 0 && (width & 3) == 0;
     };
@@ -856,6 +957,24 @@ cudaError_t run_linear_bwd(const RglRows* G, int N, const RglRows* mask, const R
     const int grid = a.ntiles < cap ? a.ntiles : cap;
     rows_linear_bwd_kernel<<<grid, 256, smem, st>>>(a);
     return cudaGetLastError();
+}
+
+// Both Linear layers of a two-layer embedding MLP (w_r / w_h: K0 -> 64 -> 32, relu after each) in one launch:
+//   G = gX . (X > 0) [R,32];  dW1 += G^T hidden, db1 += colsum G;  Hg = (G W1) . (hidden > 0) (never written);
+//   dW0 += Hg^T x0, db0 += colsum Hg.
+cudaError_t run_mlp2_bwd(const RglRows* G, const RglRows* mask, const RglRows* hidden, const float* W1, const RglRows* X0, int K0,
+                         float* dW1, float* db1, float* dW0, float* db0, int R, int num_sms, size_t max_smem, cudaStream_t st) {
+    LinBwdArgs a;
+    a.G = to_rows(G); a.mask = to_rows(mask); a.Xin = to_rows(hidden); a.Gin = to_rows(nullptr);
+    a.N = 32; a.K = 64; a.R = R; a.W = W1; a.w_layout = 0; a.accumulate = 0; a.dW = dW1; a.db = db1;
+    a.X0 = to_rows(X0); a.K0 = K0; a.dW0 = dW0; a.db0 = db0;
+    auto vec_ok = [](const Rows& r, int width) {
+        return r.ptr != nullptr && (reinterpret_cast<uintptr_t>(r.ptr) & 15u) == 0 && (r.ld & 3) == 0 && (r.gstride & 3) == 0 && (width & 3) == 0;
+    };
+    a.vecG = vec_ok(a.G, 32) && (a.mask.ptr == nullptr || vec_ok(a.mask, 32));
+    a.vecX = vec_ok(a.Xin, 64);
+    a.vecW = (reinterpret_cast<uintptr_t>(W1) & 15u) == 0;
+    return dispatch_bwd_mma(a, num_sms, max_smem, st);
 }
 
 cudaError_t run_attn_layer_bwd(const float* A, const float* Hprev, const float* gM, const float* gH, int skip, float* gHprev,

@@ -40,6 +40,15 @@ def _linear_bwd(G, N, Xin, K, R, W=None, w_layout=0, mask=None, Gin=None, accumu
     ops._count(1)
 
 
+def _mlp2_bwd(G, mask, hidden, X0, K0, R, mlp, Gf, dev):
+    """Both Linear layers of an embedding MLP (mlp[0]: K0 -> 64, mlp[2]: 64 -> 32) in one launch (rgl_mlp2_bwd)."""
+    rc = _lib.lib().rgl_mlp2_bwd(ctypes.byref(G), ctypes.byref(mask), ctypes.byref(hidden), _lib.ptr(mlp[2].weight), ctypes.byref(X0), K0,
+                                 _lib.ptr(Gf(mlp[2].weight)), _lib.ptr(Gf(mlp[2].bias)), _lib.ptr(Gf(mlp[0].weight)), _lib.ptr(Gf(mlp[0].bias)),
+                                 R, _lib.stream_ptr(dev))
+    _lib.check(rc, 'rgl_mlp2_bwd')
+    ops._count(1)
+
+
 def _carve(sizes, dev, zero=False):
     """One flat fp32 allocation carved into 16-byte aligned 1-D views (1 alloc / 1 fill instead of one per tensor)."""
     flat = (torch.zeros if zero else torch.empty)(sum((x + 3) & ~3 for x in sizes), dtype=torch.float32, device=dev)
@@ -121,8 +130,8 @@ def _graph_backward(g, sv, robot, humans, gH, G, dev, top_rows=None):
     n, L = Nh + 1, g.num_layer
     skip = bool(g.skip_connection)
     lib = _lib.lib()
-    t = _carve([B * n * n, B * n * 32, B * n * 32, B * 64, B * Nh * 64] + [B * n * 32] * L, dev)
-    gA, gM, gY, ga_r, ga_h = t[0].view(B, n, n), t[1].view(B, n, 32), t[2].view(B, n, 32), t[3].view(B, 64), t[4].view(B * Nh, 64)
+    t = _carve([B * n * n, B * n * 32, B * n * 32, 0, 0] + [B * n * 32] * L, dev)
+    gA, gM, gY = t[0].view(B, n, n), t[1].view(B, n, 32), t[2].view(B, n, 32)
     if sv['tc']:
         # H_l = relu(A Z) (+ H_{l-1}), Z = H_{l-1} W_l:   gZ = A^T (gH . mask),  gA += (gH . mask) Z^T,
         #                                                 dW_l = H_{l-1}^T gZ,    gH_{l-1} = gZ W_l^T (+ gH)
@@ -166,13 +175,9 @@ def _graph_backward(g, sv, robot, humans, gH, G, dev, top_rows=None):
     cur, side = torch.cuda.current_stream(dev), _bwd_side_stream(dev)
     side.wait_stream(cur)
     with torch.cuda.stream(side):
-        _linear_bwd(_rows(gX, 32, 1, n * 32), 32, sv['a1r'], 64, B, W=g.w_r[2].weight, mask=_rows(sv['X'], 32, 1, n * 32),
-                    Gin=_rows(ga_r, 64), dW=G(g.w_r[2].weight), db=G(g.w_r[2].bias), dev=dev)
-        _linear_bwd(_rows(ga_r, 64), 64, _rows(robot, 9), 9, B, mask=sv['a1r'], dW=G(g.w_r[0].weight), db=G(g.w_r[0].bias), dev=dev)
-    _linear_bwd(_rows(gX, 32, Nh, n * 32, offset=32), 32, sv['a1h'], 64, B * Nh, W=g.w_h[2].weight,
-                mask=_rows(sv['X'], 32, Nh, n * 32, offset=32), Gin=_rows(ga_h, 64), dW=G(g.w_h[2].weight), db=G(g.w_h[2].bias), dev=dev)
-    _linear_bwd(_rows(ga_h, 64), 64, _rows(humans, 5), 5, B * Nh, mask=sv['a1h'], dW=G(g.w_h[0].weight),
-                db=G(g.w_h[0].bias), dev=dev)
+        _mlp2_bwd(_rows(gX, 32, 1, n * 32), _rows(sv['X'], 32, 1, n * 32), sv['a1r'], _rows(robot, 9), 9, B, g.w_r, G, dev)
+    _mlp2_bwd(_rows(gX, 32, Nh, n * 32, offset=32), _rows(sv['X'], 32, Nh, n * 32, offset=32), sv['a1h'], _rows(humans, 5), 5, B * Nh,
+              g.w_h, G, dev)
     cur.wait_stream(side)           # every buffer the side branch touched outlives this join
 
 

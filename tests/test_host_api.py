@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(handle, name), name
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     lib = _lib.lib()
-    assert lib.rgl_version() == 201
+    assert lib.rgl_version() == 202
     # FMA section (SURVEY.md 2b parameter inventory + 8 pad floats per 32-wide row, rounded to 64 floats) + the tcgen05
     # operand section (hi/lo tf32 tiles: 2048 + 8192 + 4096 + 2048 + 256 floats)
     assert lib.rgl_packed_graph_floats(2) == ((8256 + 224 * 8 + 63) // 64) * 64 + 16640
