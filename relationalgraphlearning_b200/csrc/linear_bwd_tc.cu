@@ -291,13 +291,23 @@ __global__ void __launch_bounds__(128, KA == 1 ? 3 : 2) rows_linear_bwd_tc_kerne
             for (int n = 0; n < 32; ++n) scratch[m * 33 + n] = __uint_as_float(d[n]);
         }
         __syncthreads();
-        // every thread flushes 8 KA elements (hi part + lo part), consecutive threads = consecutive addresses of dW
+        // every thread flushes 8 KA elements (hi part + lo part) as 2 KA vector reductions of four consecutive addresses of dW
 #pragma unroll
-        for (int i = 0; i < 8 * KA; ++i) {
-            const int idx = tid + 128 * i;
-            const int f = a.w_layout == 0 ? (idx & (KL - 1)) : (idx >> 5), n = a.w_layout == 0 ? idx / KL : (idx & 31);
-            const float v = scratch[f * 33 + n] + scratch[(KL + f) * 33 + n];
-            atomicAdd(a.dW + (a.w_layout == 0 ? (size_t)n * KL + f : (size_t)f * 32 + n), v);
+        for (int i = 0; i < 2 * KA; ++i) {
+            const int idx = (tid + 128 * i) * 4;
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int f = a.w_layout == 0 ? ((idx + j) & (KL - 1)) : (idx >> 5), n = a.w_layout == 0 ? idx / KL : ((idx + j) & 31);
+                v[j] = scratch[f * 33 + n] + scratch[(KL + f) * 33 + n];
+            }
+            float* dst = a.dW + idx;            // both layouts: element idx of the dense [.][.] matrix
+            if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) atomicAdd(dst + j, v[j]);
+            }
         }
     }
     if (a.db && it > 0) atomicAdd(a.db + lane, bacc);

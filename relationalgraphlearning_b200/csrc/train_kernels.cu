@@ -522,16 +522,55 @@ __global__ void __launch_bounds__(256, (DB || MROWS <= 32) ? 2 : 1) rows_linear_
         if (!DB && next < a.ntiles) stage(next, 0);
     }
     // ---- flush the per-CTA partial sums: accumulator fragment (m16n8): [0],[1] = row g, cols 2t, 2t+1; [2],[3] = row g+8 ----
+    // Each warp transposes its (16 x 8) fragment through 1 KB of the now idle staging memory so that a lane owns four consecutive
+    // elements of dW and issues ONE 16-byte vector reduction (REDG.E.ADD.F32x4) for them: a quarter of the reduction
+    // instructions (value layer 2: 256 CTAs x 10 000 elements; 19.6 -> 18.2 us per launch).
     if (a.dW) {
+        float* scr = Gs0 + warp * 256;
 #pragma unroll
         for (int i = 0; i < TW; ++i) {
             const int id = warp + 8 * i;
             if (WT % 8 == 0 || id < WT) {
                 const int mt = id / N8, nt = id - mt * N8;
+                if (a.w_layout == 0 && (K & 3)) {       // rows of dW not 16-byte aligned (K = 5, 9): scalar reductions from the fragment
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int k = mt * 16 + g + 8 * (c >> 1), nn = nt * 8 + 2 * t + (c & 1);
-                    if (k < K && nn < N) atomicAdd(a.dW + (a.w_layout == 0 ? (size_t)nn * K + k : (size_t)k * N + nn), wacc[i][c]);
+                    for (int c = 0; c < 4; ++c) {
+                        const int k = mt * 16 + g + 8 * (c >> 1), nn = nt * 8 + 2 * t + (c & 1);
+                        if (k < K && nn < N) atomicAdd(a.dW + (size_t)nn * K + k, wacc[i][c]);
+                    }
+                    continue;
+                }
+                float4 v;
+                size_t off;
+                int left;                   // valid elements among the lane's four (<= 0: none)
+                if (a.w_layout == 0) {      // dW[nn][k]: k contiguous.  scratch [8 n][20]
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) scr[(2 * t + (c & 1)) * 20 + g + 8 * (c >> 1)] = wacc[i][c];
+                    __syncwarp();
+                    const int nl = lane >> 2, k4 = (lane & 3) * 4;
+                    v = lds128(scr + nl * 20 + k4);
+                    const int nn = nt * 8 + nl, k = mt * 16 + k4;
+                    off = (size_t)nn * K + k;
+                    left = nn < N ? K - k : 0;
+                } else {                    // dW[k][nn]: nn contiguous.  scratch [16 k][12]
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) scr[(g + 8 * (c >> 1)) * 12 + 2 * t + (c & 1)] = wacc[i][c];
+                    __syncwarp();
+                    const int kl = lane >> 1, n4 = (lane & 1) * 4;
+                    v = lds128(scr + kl * 12 + n4);
+                    const int k = mt * 16 + kl, nn = nt * 8 + n4;
+                    off = (size_t)k * N + nn;
+                    left = k < K ? N - nn : 0;
+                }
+                __syncwarp();
+                float* dst = a.dW + off;
+                if (left >= 4 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+                } else {
+                    if (left > 0) atomicAdd(dst, v.x);
+                    if (left > 1) atomicAdd(dst + 1, v.y);
+                    if (left > 2) atomicAdd(dst + 2, v.z);
+                    if (left > 3) atomicAdd(dst + 3, v.w);
                 }
             }
         }

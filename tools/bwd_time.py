@@ -13,6 +13,7 @@ shapes = [('value L3 (1,100)', B, 1, 100, True, False, 0, False), ('value L2 (10
           ('w_h.2 (32,64) R=B*nh', B * nh, 32, 64, True, True, 0, False), ('w_h.0 (64,5) R=B*nh', B * nh, 64, 5, True, True, 0, False),
           ('w_r.2 (32,64) R=B', B, 32, 64, True, True, 0, False), ('w_r.0 (64,9) R=B', B, 64, 9, True, True, 0, False)]
 only = os.environ.get('BWD_ONLY')
+nodw, nodx = os.environ.get('BWD_NODW'), os.environ.get('BWD_NODX')     # experiments: data gradient only / weight gradient only
 for si, (name, R, N, K, bias, mask, layout, accum) in enumerate(shapes):
     if only is not None and si != int(only):
         continue
@@ -27,7 +28,8 @@ for si, (name, R, N, K, bias, mask, layout, accum) in enumerate(shapes):
     db = torch.zeros(N, device=dev) if bias else None
     def run():
         T._linear_bwd(T._rows(G, ldN), N, T._rows(X, ldK), K, R, W=W, w_layout=layout, mask=T._rows(M, ldN) if mask else None,
-                      Gin=T._rows(Gin, ldK) if K > 9 else None, accumulate=accum, dW=dW, db=db, dev=dev)
+                      Gin=T._rows(Gin, ldK) if (K > 9 and not nodx) else None, accumulate=accum, dW=None if nodw else dW,
+                      db=None if nodw else db, dev=dev)
     for _ in range(5): run()
     torch.cuda.synchronize()
     if only is not None:
