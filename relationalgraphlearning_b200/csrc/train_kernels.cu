@@ -227,7 +227,12 @@ __global__ void __launch_bounds__(256, (DB || MROWS <= 32) ? 2 : 1) rows_linear_
     constexpr int ldg = ((NP + 31) / 32) * 32 + 8, ldx = ((KP + 31) / 32) * 32 + 8;      // = 8 mod 32 words
     constexpr int WPR = 8 / (MROWS / 16);   // warps sharing a 16-row block in the data gradient (1 or 2): they split the k columns
     constexpr int KPW = (K8 + WPR - 1) / WPR;                // k column tiles per warp in the data gradient
-    constexpr int WT = K16 * N8, TW = (WT + 7) / 8;          // (16 x 8) tiles of dW; tile id = warp + 8 i
+    // (16 x 8) tiles of dW, dealt to the warps as a WM x WN grid: warp (wm, wn) owns the tiles (mt, nt) = (wm + WM j, wn + WN q).
+    // Every A fragment (X^T, 16 input columns x 8 rows) is split once and reused for the warp's NTW output-column tiles, every
+    // B fragment (G) for its MTW tiles -- the first version dealt the tiles round-robin and re-split both operands per tile
+    // (100 x 100 layer: 72 splits and 72 fragment loads per k-step and warp, now 22).
+    constexpr int WM = K16 >= 8 ? 8 : (K16 >= 4 ? 4 : (K16 >= 2 ? 2 : 1)), WN = 8 / WM;
+    constexpr int MTW = (K16 + WM - 1) / WM, NTW = (N8 + WN - 1) / WN, TW = MTW * NTW;
     constexpr int ld0 = 24;                                  // x0 tile: 16 columns (K0 <= 16, zero padded), stride = 24 mod 32 words
     constexpr int tileG = MROWS * ldg, tileX = MROWS * ldx, tile0 = F0 ? MROWS * ld0 : 0, stage_floats = 2 * tileG + tileX + tile0;
     constexpr int n4 = NP / 4, k4 = KP / 4;
@@ -432,36 +437,38 @@ __global__ void __launch_bounds__(256, (DB || MROWS <= 32) ? 2 : 1) rows_linear_
         // ---- weight gradient: the rows of the tile are the contraction ----
         auto weight_grad = [&]() {
         if (a.dW) {
+            const int wm = warp % WM, wn = warp / WM;
+#pragma unroll 2
+            for (int ks = 0; ks < MROWS / 8; ++ks) {
+                uint32_t ahi[MTW][4], alo[MTW][4];
 #pragma unroll
-            for (int i = 0; i < TW; ++i) {
-                const int id = warp + 8 * i;
-                if (WT % 8 == 0 || id < WT) {
-                    const int mt = id / N8, nt = id - mt * N8;
-                    const float* xp = Xs + t * ldx + mt * 16 + g;
-                    const float* gp = Gs + t * ldg + nt * 8 + g;
-                    // two accumulators: even / odd k-steps (halves the dependent HMMA chain)
-                    float w2[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-                    for (int ks = 0; ks < MROWS / 8; ++ks) {
-                        uint32_t ahi[4], alo[4], bh0, bl0, bh1, bl1;
-                        split_tf32(xp[(ks * 8) * ldx], ahi[0], alo[0]);
-                        split_tf32(xp[(ks * 8) * ldx + 8], ahi[1], alo[1]);
-                        split_tf32(xp[(ks * 8 + 4) * ldx], ahi[2], alo[2]);
-                        split_tf32(xp[(ks * 8 + 4) * ldx + 8], ahi[3], alo[3]);
-                        split_tf32(gp[(ks * 8) * ldg], bh0, bl0);
-                        split_tf32(gp[(ks * 8 + 4) * ldg], bh1, bl1);
-                        if (ks & 1) {
-                            mma_tf32(w2, alo, bh0, bh1);
-                            mma_tf32(w2, ahi, bl0, bl1);
-                            mma_tf32(w2, ahi, bh0, bh1);
-                        } else {
-                            mma_tf32(wacc[i], alo, bh0, bh1);
-                            mma_tf32(wacc[i], ahi, bl0, bl1);
-                            mma_tf32(wacc[i], ahi, bh0, bh1);
+                for (int jm = 0; jm < MTW; ++jm) {
+                    const int mt = wm + WM * jm;
+                    if (K16 % WM == 0 || mt < K16) {
+                        const float* xp = Xs + (ks * 8 + t) * ldx + mt * 16 + g;
+                        split_tf32(xp[0], ahi[jm][0], alo[jm][0]);
+                        split_tf32(xp[8], ahi[jm][1], alo[jm][1]);
+                        split_tf32(xp[4 * ldx], ahi[jm][2], alo[jm][2]);
+                        split_tf32(xp[4 * ldx + 8], ahi[jm][3], alo[jm][3]);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < NTW; ++q) {
+                    const int nt = wn + WN * q;
+                    if (N8 % WN == 0 || nt < N8) {
+                        const float* gp = Gs + (ks * 8 + t) * ldg + nt * 8 + g;
+                        uint32_t bh0, bl0, bh1, bl1;
+                        split_tf32(gp[0], bh0, bl0);
+                        split_tf32(gp[4 * ldg], bh1, bl1);
+#pragma unroll
+                        for (int jm = 0; jm < MTW; ++jm) {
+                            if (K16 % WM == 0 || wm + WM * jm < K16) {
+                                mma_tf32(wacc[jm * NTW + q], alo[jm], bh0, bh1);
+                                mma_tf32(wacc[jm * NTW + q], ahi[jm], bl0, bl1);
+                                mma_tf32(wacc[jm * NTW + q], ahi[jm], bh0, bh1);
+                            }
                         }
                     }
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) wacc[i][c] += w2[c];
                 }
             }
         }
@@ -529,9 +536,8 @@ __global__ void __launch_bounds__(256, (DB || MROWS <= 32) ? 2 : 1) rows_linear_
         float* scr = Gs0 + warp * 256;
 #pragma unroll
         for (int i = 0; i < TW; ++i) {
-            const int id = warp + 8 * i;
-            if (WT % 8 == 0 || id < WT) {
-                const int mt = id / N8, nt = id - mt * N8;
+            const int mt = warp % WM + WM * (i / NTW), nt = warp / WM + WN * (i % NTW);
+            if (mt < K16 && nt < N8) {
                 if (a.w_layout == 0 && (K & 3)) {       // rows of dW not 16-byte aligned (K = 5, 9): scalar reductions from the fragment
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
