@@ -234,3 +234,49 @@ def test_tcgen05_linear_backward_forced_on_every_shape(cuda_device):
     assert out.returncode == 0, out.stderr[-2000:]
     worst = float(out.stdout.strip().split('WORST')[-1])
     assert worst < 2e-6, out.stdout                       # 3xTF32: fp32-level agreement with the float64 reference
+
+
+@pytest.mark.parametrize('R,K0,grouped', [(700, 5, False), (4000, 9, False), (23000, 5, True), (64, 9, True)])
+def test_fused_embedding_mlp_backward_matches_float64(R, K0, grouped, cuda_device):
+    """rgl_mlp2_bwd (both Linear layers of w_r / w_h in one launch, hidden gradient kept on chip) against float64 autograd of
+    relu(relu(x0 W0^T + b0) W1^T + b1) -- graph_model.py:41-42, helpers.py:5-13 with last_relu=True."""
+    import ctypes
+    from relationalgraphlearning_b200 import _lib
+    dev = cuda_device
+    gen = torch.Generator().manual_seed(R + K0)
+    rnd = lambda *s: torch.randn(*s, generator=gen)   # noqa: E731
+    W0, b0, W1, b1 = rnd(64, K0) * 0.5, rnd(64) * 0.1, rnd(32, 64) * 0.2, rnd(32) * 0.1
+    n = 11
+    if grouped:      # the rows are nodes 1..n-1 of every state inside [B, n, .] tensors, as the human branch addresses them
+        Bq = max(1, R // (n - 1)); R = Bq * (n - 1)
+    x0, gX = rnd(R, K0), rnd(R, 32)
+    # float64 reference
+    p = [t.double().requires_grad_(True) for t in (W0, b0, W1, b1)]
+    hid = torch.relu(x0.double() @ p[0].t() + p[1])
+    X = torch.relu(hid @ p[2].t() + p[3])
+    X.backward(gX.double())
+    hid32, X32 = hid.detach().float(), X.detach().float()
+    if grouped:
+        def embed(t, w):      # place rows into nodes 1..n-1 of a [Bq, n, w] tensor (node 0 = garbage the kernel must not touch)
+            full = torch.full((Bq, n, w), 7.0)
+            full[:, 1:, :] = t.view(Bq, n - 1, w)
+            return full.to(dev)
+        gXd, Xd, hd = embed(gX, 32), embed(X32, 32), embed(hid32, 64)
+        rG, rM = training._rows(gXd, 32, n - 1, n * 32, offset=32), training._rows(Xd, 32, n - 1, n * 32, offset=32)
+        rH = training._rows(hd, 64, n - 1, n * 64, offset=64)
+    else:
+        gXd, Xd, hd = gX.to(dev), X32.to(dev), hid32.to(dev)
+        rG, rM, rH = training._rows(gXd, 32), training._rows(Xd, 32), training._rows(hd, 64)
+    x0d = x0.to(dev).contiguous()
+    W1d = W1.to(dev)
+    dW1, db1, dW0, db0 = (torch.zeros(32, 64, device=dev), torch.zeros(32, device=dev), torch.zeros(64, K0, device=dev),
+                          torch.zeros(64, device=dev))
+    r0 = training._rows(x0d, K0)
+    with torch.cuda.device(dev):
+        rc = _lib.lib().rgl_mlp2_bwd(ctypes.byref(rG), ctypes.byref(rM), ctypes.byref(rH), _lib.ptr(W1d), ctypes.byref(r0), K0,
+                                     _lib.ptr(dW1), _lib.ptr(db1), _lib.ptr(dW0), _lib.ptr(db0), R, _lib.stream_ptr(dev))
+    _lib.check(rc, 'rgl_mlp2_bwd')
+    torch.cuda.synchronize(dev)
+    for got, ref, what in ((dW1, p[2].grad, 'dW1'), (db1, p[3].grad, 'db1'), (dW0, p[0].grad, 'dW0'), (db0, p[1].grad, 'db0')):
+        err = float((got.double().cpu() - ref).abs().max() / ref.abs().max())
+        assert err < 2e-5, (what, err)            # 3xTF32 products, fp32 accumulation over R rows
