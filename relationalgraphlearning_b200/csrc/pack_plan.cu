@@ -37,43 +37,69 @@ __device__ __forceinline__ void tc_put(float* tile, int lo_off, int row, int k, 
     tile[lo_off + idx] = rna_tf32f(w - hi);
 }
 
-__device__ void pack_graph_tc(const RglGraphParams& p, float* tc, int t, int nt) {
-    for (int idx = t; idx < HID * 16; idx += nt) {          // emb layer 1: k-concatenated robot | human | biases; hi at k, lo at k + 16
-        const int u = idx >> 4, k = idx & 15;
-        const float w = k < RD ? p.wr0_w[u * RD + k] : k < RD + HD ? p.wh0_w[u * HD + (k - RD)] : k == 14 ? p.wr0_b[u] : p.wh0_b[u];
-        const float hi = rna_tf32f(w);
-        tc[T_W0 + u * 32 + ((((k >> 2) ^ u) & 7) << 2) + (k & 3)] = hi;
-        tc[T_W0 + u * 32 + (((((k + 16) >> 2) ^ u) & 7) << 2) + (k & 3)] = rna_tf32f(w - hi);
-    }
-    for (int idx = t; idx < 64 * HID; idx += nt) {          // emb layer 2: n-stacked human (rows 0-31) | robot (rows 32-63)
-        const int row = idx / HID, k = idx - row * HID;
-        const float w = row < XD ? p.wh1_w[row * HID + k] : p.wr1_w[(row - XD) * HID + k];
-        tc_put(tc + T_W1 + (k >> 5) * 2048, 4096, row, k & 31, w);
-    }
-    for (int idx = t; idx < XD * XD; idx += nt) {           // X @ W uses W[k][n]: B operand row n holds column n
-        const int nn = idx >> 5, k = idx & 31;
-        tc_put(tc + T_WA, 2048, nn, k, p.w_a[k * XD + nn]);
-        tc_put(tc + T_WA, 2048, XD + nn, k, p.Ws[0][k * XD + nn]);
-        for (int l = 1; l < p.num_layer; ++l) tc_put(tc + T_WS1 + (l - 1) * 2048, 1024, nn, k, p.Ws[l][k * XD + nn]);
-    }
-    float* b = tc + tc_bias_off(p.num_layer);
-    for (int idx = t; idx < 256; idx += nt)
-        b[idx] = idx < XD ? p.wh1_b[idx] : (idx >= TC_RBIAS && idx < TC_RBIAS + XD) ? p.wr1_b[idx - TC_RBIAS] : 0.f;
-}
-
+// One section per CTA (group): the sections are independent gathers of a few hundred to a few thousand floats, each ONE global
+// round trip deep.  The first version ran them one after the other in every thread (12 dependent round trips, 8 us per
+// launch at the head of every training step, where the weights change and the blob is re-packed); now they run side by side.
 __global__ void pack_graph_kernel(RglGraphParams p, float* out) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
-    pack_graph_tc(p, out + graph_tc_off(p.num_layer), t, nt);
-    pack_linear_T(out + G_WR0, p.wr0_w, HID, RD, HID, t, nt);
-    pack_copy(out + G_BR0, p.wr0_b, HID, HID, t, nt);
-    pack_linear_T(out + G_WR1, p.wr1_w, XD, HID, LDW, t, nt);
-    pack_copy(out + G_BR1, p.wr1_b, XD, XD, t, nt);
-    pack_linear_T(out + G_WH0, p.wh0_w, HID, HD, HID, t, nt);
-    pack_copy(out + G_BH0, p.wh0_b, HID, HID, t, nt);
-    pack_linear_T(out + G_WH1, p.wh1_w, XD, HID, LDW, t, nt);
-    pack_copy(out + G_BH1, p.wh1_b, XD, XD, t, nt);
-    pack_rows(out + G_WA, p.w_a, XD, XD, LDW, t, nt);
-    for (int l = 0; l < p.num_layer; ++l) pack_rows(out + G_WS + l * XD * LDW, p.Ws[l], XD, XD, LDW, t, nt);
+    float* tc = out + graph_tc_off(p.num_layer);
+    int sec = blockIdx.x, sub = 0, nsub = 1;
+    // sections 1 (embedding layer 2 tiles), 6 and 8 (k-major embedding layer 2) are split over several CTAs
+    if (sec >= 1 && sec < 5) { sub = sec - 1; nsub = 4; sec = 1; }
+    else if (sec >= 5) {
+        sec -= 3;                                             // 2, 3, 4, 5, [6, 6], 7, [8, 8], 9, 10 + l
+        if (sec == 6 || sec == 7) { sub = sec - 6; nsub = 2; sec = 6; }
+        else if (sec == 8) sec = 7;
+        else if (sec == 9 || sec == 10) { sub = sec - 9; nsub = 2; sec = 8; }
+        else if (sec > 10) sec -= 2;
+    }
+    const int t = sub * blockDim.x + threadIdx.x, nt = nsub * blockDim.x;
+    switch (sec) {
+    case 0:
+        for (int idx = t; idx < HID * 16; idx += nt) {          // emb layer 1: k-concatenated robot | human | biases; hi at k, lo at k + 16
+            const int u = idx >> 4, k = idx & 15;
+            const float w = k < RD ? p.wr0_w[u * RD + k] : k < RD + HD ? p.wh0_w[u * HD + (k - RD)] : k == 14 ? p.wr0_b[u] : p.wh0_b[u];
+            const float hi = rna_tf32f(w);
+            tc[T_W0 + u * 32 + ((((k >> 2) ^ u) & 7) << 2) + (k & 3)] = hi;
+            tc[T_W0 + u * 32 + (((((k + 16) >> 2) ^ u) & 7) << 2) + (k & 3)] = rna_tf32f(w - hi);
+        }
+        break;
+    case 1:
+        for (int idx = t; idx < 64 * HID; idx += nt) {          // emb layer 2: n-stacked human (rows 0-31) | robot (rows 32-63)
+            const int row = idx / HID, k = idx - row * HID;
+            const float w = row < XD ? p.wh1_w[row * HID + k] : p.wr1_w[(row - XD) * HID + k];
+            tc_put(tc + T_W1 + (k >> 5) * 2048, 4096, row, k & 31, w);
+        }
+        break;
+    case 2:
+        for (int idx = t; idx < XD * XD; idx += nt) {           // X @ W uses W[k][n]: B operand row n holds column n
+            const int nn = idx >> 5, k = idx & 31;
+            tc_put(tc + T_WA, 2048, nn, k, p.w_a[k * XD + nn]);
+            tc_put(tc + T_WA, 2048, XD + nn, k, p.Ws[0][k * XD + nn]);
+            for (int l = 1; l < p.num_layer; ++l) tc_put(tc + T_WS1 + (l - 1) * 2048, 1024, nn, k, p.Ws[l][k * XD + nn]);
+        }
+        break;
+    case 3: {
+        float* b = tc + tc_bias_off(p.num_layer);
+        for (int idx = t; idx < 256; idx += nt)
+            b[idx] = idx < XD ? p.wh1_b[idx] : (idx >= TC_RBIAS && idx < TC_RBIAS + XD) ? p.wr1_b[idx - TC_RBIAS] : 0.f;
+        break;
+    }
+    case 4:                                                     // the four bias vectors of the k-major (fp32-FMA) section
+        pack_copy(out + G_BR0, p.wr0_b, HID, HID, t, nt);
+        pack_copy(out + G_BR1, p.wr1_b, XD, XD, t, nt);
+        pack_copy(out + G_BH0, p.wh0_b, HID, HID, t, nt);
+        pack_copy(out + G_BH1, p.wh1_b, XD, XD, t, nt);
+        break;
+    case 5: pack_linear_T(out + G_WR0, p.wr0_w, HID, RD, HID, t, nt); break;
+    case 6: pack_linear_T(out + G_WR1, p.wr1_w, XD, HID, LDW, t, nt); break;
+    case 7: pack_linear_T(out + G_WH0, p.wh0_w, HID, HD, HID, t, nt); break;
+    case 8: pack_linear_T(out + G_WH1, p.wh1_w, XD, HID, LDW, t, nt); break;
+    case 9: pack_rows(out + G_WA, p.w_a, XD, XD, LDW, t, nt); break;
+    default: {
+        const int l = sec - 10;
+        if (l < p.num_layer) pack_rows(out + G_WS + l * XD * LDW, p.Ws[l], XD, XD, LDW, t, nt);
+    }
+    }
 }
 
 __global__ void pack_value_kernel(RglValueParams p, float* out) {
@@ -333,7 +359,7 @@ __global__ void plan_backup_kernel(const float* __restrict__ v, const float* __r
 }
 
 cudaError_t run_pack_graph(const RglGraphParams& p, float* out, cudaStream_t st) {
-    pack_graph_kernel<<<8, 256, 0, st>>>(p, out);
+    pack_graph_kernel<<<15 + p.num_layer, 256, 0, st>>>(p, out);      // 15 section CTAs + one per GCN layer
     return cudaGetLastError();
 }
 cudaError_t run_pack_value(const RglValueParams& p, float* out, cudaStream_t st) {
