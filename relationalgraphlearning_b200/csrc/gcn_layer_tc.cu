@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) gcn_layer_tc_kernel(c
     const int s_loc = gt / n;
     const bool row_used = gt < SPT * n;
     const uint32_t my_row = gl_row_ptr(xf_s, gt);
-    const int srow0 = s_loc * n;                         // first row of this thread's state
+    const int srow0 = (row_used ? s_loc : 0) * n;        // first row of this thread's state (tail rows: state 0, reads stay inside the buffer)
     const int tstride = gridDim.x * G;
 
     for (int tile = blockIdx.x * G + grp; tile < ntiles; tile += tstride) {
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) gcn_layer_tma_kernel(
 
     const int s_loc = gt / n;
     const bool row_used = gt < SPT * n;
-    const int srow0 = s_loc * n;
+    const int srow0 = (row_used ? s_loc : 0) * n;        // tail rows read state 0: every read stays inside the row buffers
     const int tstride = gridDim.x * G;
     const int rows_tile = SPT * n;
     const uint32_t tile_bytes = (uint32_t)rows_tile * 128u;

@@ -91,7 +91,10 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tc_kern
     const int hum = is_robot ? 0 : hrow - s_loc * Nh;                 // human index
     const bool row_used = gt < SPT * n;
     const int node = is_robot ? 0 : hum + 1;
-    const int hbase = SPT + s_loc * Nh;                               // first human row of this thread's state
+    // rows of this thread's state in the group's row buffer.  The tile's tail rows (gt >= SPT * n) run the per-state loops and drop
+    // the result; they read state 0's rows so that every read stays inside the buffer
+    const int s_rd = row_used ? s_loc : 0;
+    const int hbase = SPT + s_rd * Nh;                                // first human row of this thread's state
 
     const int ntiles = a.ntiles;
     const int tstride = gridDim.x * G;
@@ -297,7 +300,7 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tc_kern
 #pragma unroll
                     for (int j = 0; j < NMAX; ++j) {
                         if (N > 0 || j < n) {
-                            const uint32_t rp = row_ptr(xf_s, j == 0 ? s_loc : hbase + j - 1);
+                            const uint32_t rp = row_ptr(xf_s, j == 0 ? s_rd : hbase + j - 1);
                             f32x2 d01 = 0ull, d23 = 0ull;           // four partial sums, two per packed FFMA2
 #pragma unroll
                             for (int c = 0; c < 8; ++c) {
@@ -351,7 +354,7 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tc_kern
 #pragma unroll
                 for (int j = 0; j < NMAX; ++j) {
                     if (N > 0 || j < n) {
-                        const uint32_t rp = row_ptr(xf_s, j == 0 ? s_loc : hbase + j - 1);
+                        const uint32_t rp = row_ptr(xf_s, j == 0 ? s_rd : hbase + j - 1);
                         const f32x2 pj = pack2(p[j], p[j]);
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {

@@ -93,7 +93,10 @@ __global__ void __launch_bounds__(128 * G, G <= 2 ? 2 : 1) graph_forward_tp_kern
     const bool row_used = s_loc < SPT && node < N;                    // padding rows (odd n) and the tile's tail rows idle
     const bool is_robot = node == 0;
     const int hum = node - 1;                                         // human index (node >= 1)
-    const int sbase = s_loc * NP;                                     // first row of this thread's state
+    // first row of this thread's state.  The tile's tail rows (s_loc == SPT: 128 is no multiple of NP) run the per-state loops
+    // like everyone else and drop the result; they read state 0's rows so that every read stays inside the group's row buffer
+    // (compute-sanitizer racecheck: with sbase = s_loc * NP they read up to N - 1 rows past it, into the save staging area)
+    const int sbase = (s_loc < SPT ? s_loc : 0) * NP;
     const bool odd = gt & 1;                                          // lane parity: which 16-column half this thread computes
 
     const int ntiles = a.ntiles;
