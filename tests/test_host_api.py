@@ -150,3 +150,27 @@ def test_argument_validation_of_the_round2_entry_points():
     assert b'rgl_comm_create' in lib.rgl_comm_last_error_string()
     assert lib.rgl_comm_handle_bytes() == 64
     assert lib.rgl_comm_destroy(None) == 0
+
+
+def test_argument_validation_of_the_training_backward_entry_points():
+    """The staged attention / similarity backward and the fused embedding-MLP backward reject bad arguments before any launch."""
+    lib = _lib.lib()
+    buf = (ctypes.c_float * 64)()
+    p = ctypes.cast(buf, ctypes.POINTER(ctypes.c_float))
+    # rgl_attn_sim_bwd(A, Z, gM, mask, up_rows, gA_in, gZ, gA_out, X, Y, gY, gX, gx_accumulate, B, n, stream)
+    assert lib.rgl_attn_sim_bwd(None, None, None, None, 1, None, None, None, None, None, None, None, 0, 4, 6, None) == -1      # nulls
+    assert lib.rgl_attn_sim_bwd(None, None, None, None, 1, None, None, None, None, None, None, None, 0, 0, 6, None) == 0       # empty: no-op
+    assert lib.rgl_attn_sim_bwd(p, p, p, None, 7, None, p, p, None, None, None, None, 0, 4, 6, None) == -1                     # up_rows > n
+    assert lib.rgl_attn_sim_bwd(p, p, p, None, 0, None, p, p, None, None, None, None, 0, 4, 6, None) == -1                     # up_rows < 1
+    assert lib.rgl_attn_sim_bwd(p, p, p, None, 6, None, p, None, None, None, None, None, 0, 4, 6, None) == -1                  # no X and no gA_out
+    assert lib.rgl_attn_sim_bwd(p, p, p, None, 6, None, p, None, p, None, None, None, 0, 4, 6, None) == -1                     # X without Y / gY / gX
+    assert lib.rgl_attn_sim_bwd(p, p, p, None, 6, None, p, p, None, None, None, None, 0, 4, 33, None) == -1                    # n > 32
+    # rgl_attn_layer_bwd(..., mask, up_rows, stream)
+    assert lib.rgl_attn_layer_bwd(p, p, p, None, 0, p, p, 0, 4, 6, None, 0, None) == -1                                         # up_rows < 1
+    # rgl_mlp2_bwd(G, mask, hidden, W1, X0, K0, dW1, db1, dW0, db0, R, stream)
+    r = _lib.Rows()
+    r.ptr, r.ld, r.rows_per_group, r.group_stride = ctypes.addressof(buf), 32, 0, 0
+    assert lib.rgl_mlp2_bwd(None, None, None, None, None, 5, None, None, None, None, 8, None) == -1                            # nulls
+    assert lib.rgl_mlp2_bwd(None, None, None, None, None, 5, None, None, None, None, 0, None) == 0                             # empty: no-op
+    assert lib.rgl_mlp2_bwd(ctypes.byref(r), None, ctypes.byref(r), p, ctypes.byref(r), 17, p, p, p, p, 8, None) == -4          # K0 > 16: unsupported
+    assert lib.rgl_mlp2_bwd(ctypes.byref(r), None, ctypes.byref(r), p, ctypes.byref(r), 0, p, p, p, p, 8, None) == -4
