@@ -784,10 +784,12 @@ __device__ __forceinline__ void cp_async4(uint32_t dst_s, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst_s), "l"(src) : "memory");
 }
 
-template <bool SIM>
+// NT: compile-time node count (6, 11, 21: the counts of the tcgen05 forward; 0 = run-time n): the row loops unroll fully and
+// every shared-memory address becomes base + immediate.
+template <bool SIM, int NT>
 __global__ void __launch_bounds__(256) attn_sim_bwd_kernel(const AttnSimArgs a) {
     extern __shared__ __align__(16) float sm[];
-    const int n = a.n, nn = n * n, spb = a.spb;
+    const int n = NT ? NT : a.n, nn = n * n, spb = NT ? (64 / (NT ? NT : 1)) : a.spb;
     const int b0 = blockIdx.x * spb;
     const int cnt = a.B - b0 < spb ? a.B - b0 : spb;
     const int tile = spb * n * 32;
@@ -859,8 +861,7 @@ __global__ void __launch_bounds__(256) attn_sim_bwd_kernel(const AttnSimArgs a) 
         const float* Ab = As + sls * nn + js;
         float* gAb = gAs + sls * nn + js;
         const float* gMb = gMs + sls * n * 32 + 8 * q;
-#pragma unroll 2
-        for (int i = 0; i < a.up_rows; ++i) {
+        auto row = [&](int i) {
             const float aij = Ab[i * n];
             const float4 gu = lds128(gMb + i * 32), gv = lds128(gMb + i * 32 + 4);
             const float gm[8] = {gu.x, gu.y, gu.z, gu.w, gv.x, gv.y, gv.z, gv.w};
@@ -870,6 +871,13 @@ __global__ void __launch_bounds__(256) attn_sim_bwd_kernel(const AttnSimArgs a) 
             d += __shfl_xor_sync(0xffffffffu, d, 1);
             d += __shfl_xor_sync(0xffffffffu, d, 2);
             if (q == 0 && live) gAb[i * n] += d;
+        };
+        if (NT && a.up_rows == NT) {
+#pragma unroll
+            for (int i = 0; i < (NT ? NT : 1); ++i) row(i);
+        } else {
+#pragma unroll 2
+            for (int i = 0; i < a.up_rows; ++i) row(i);
         }
         if (live) {
             float4* o4 = reinterpret_cast<float4*>(a.gZ + g0 + r * 32 + 8 * q);
@@ -889,12 +897,13 @@ __global__ void __launch_bounds__(256) attn_sim_bwd_kernel(const AttnSimArgs a) 
         const float* arow = As + sl * nn + i * n;
         const float* grow = gAs + sl * nn + i * n;
         float dot = 0.f;
+#pragma unroll
         for (int k = 0; k < n; ++k) dot = fmaf(grow[k], arow[k], dot);
         float acc[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) acc[c] = 0.f;
         const float* Xb = Xs + sl * n * 32 + 8 * q;
-#pragma unroll 2
+#pragma unroll
         for (int k = 0; k < n; ++k) {
             const float gs = arow[k] * (grow[k] - dot);
             if (q == 0) gSs[sl * nn + i * n + k] = gs;
@@ -910,7 +919,7 @@ __global__ void __launch_bounds__(256) attn_sim_bwd_kernel(const AttnSimArgs a) 
     if (live) {
         const float* Yb = Ys + sl * n * 32 + 8 * q;
         const float* gsc = gSs + sl * nn + j;
-#pragma unroll 2
+#pragma unroll
         for (int i = 0; i < n; ++i) {
             const float gs = gsc[i * n];
             const float4 u = lds128(Yb + i * 32), v = lds128(Yb + i * 32 + 4);
@@ -1042,13 +1051,17 @@ cudaError_t run_attn_sim_bwd(const float* A, const float* Z, const float* gM, co
     const size_t smem = ((size_t)a.spb * n * 32 * (sim ? 5 : 3) + (size_t)a.spb * n * n * (sim ? 3 : 2)) * sizeof(float);
     if (smem > max_smem) return cudaErrorInvalidConfiguration;
     const int grid = (B + a.spb - 1) / a.spb;
+#define RGL_AS_LAUNCH(SIMV, NTV) do { \
+        if (cudaError_t e = ensure_dyn_smem(attn_sim_bwd_kernel<SIMV, NTV>, (int)max_smem)) return e; \
+        attn_sim_bwd_kernel<SIMV, NTV><<<grid, threads, smem, st>>>(a); } while (0)
     if (sim) {
-        if (cudaError_t e = ensure_dyn_smem(attn_sim_bwd_kernel<true>, (int)max_smem)) return e;
-        attn_sim_bwd_kernel<true><<<grid, threads, smem, st>>>(a);
+        if (n == 6) RGL_AS_LAUNCH(true, 6); else if (n == 11) RGL_AS_LAUNCH(true, 11); else if (n == 21) RGL_AS_LAUNCH(true, 21);
+        else RGL_AS_LAUNCH(true, 0);
     } else {
-        if (cudaError_t e = ensure_dyn_smem(attn_sim_bwd_kernel<false>, (int)max_smem)) return e;
-        attn_sim_bwd_kernel<false><<<grid, threads, smem, st>>>(a);
+        if (n == 6) RGL_AS_LAUNCH(false, 6); else if (n == 11) RGL_AS_LAUNCH(false, 11); else if (n == 21) RGL_AS_LAUNCH(false, 21);
+        else RGL_AS_LAUNCH(false, 0);
     }
+#undef RGL_AS_LAUNCH
     return cudaGetLastError();
 }
 
